@@ -1,0 +1,234 @@
+// gp_pack.cu -- gp_pack / gp_unpack_scale / gp_scale / gp_check_finite.
+//
+// Reference being replaced:
+//   chainermn/communicators/_memory_utility.py:253-268, 289-358  (batched pack)
+//   chainermn/communicators/_memory_utility.py:271-286, 361-429  (batched unpack)
+//   chainermn/communicators/pure_nccl_communicator.py:183-189    (div_by_size)
+//   chainermn/communicators/mpi_communicator_base.py:730-733     (_ensure_all_finite)
+// Layout contract (bit-exact with the reference): element k of parameter j sits
+// at flat index csum[j] + k of the packed buffer, parameters in the order the
+// caller lists them (sorted(model.namedparams()), _memory_utility.py:154-165).
+#include "gp_walk.cuh"
+
+namespace {
+
+template <class P> __device__ __forceinline__ const P* cptr(uint64_t p) {
+  return reinterpret_cast<const P*>(p);
+}
+template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
+  return reinterpret_cast<P*>(p);
+}
+
+// buffer[buf_off + k] = (B)(scale * ptr0[k])
+struct PackOp {
+  static constexpr int kMaxUnroll = 4;
+  void* buffer;
+  ScaleArg s;
+
+  static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
+
+  template <class B, class P, class CP>
+  __device__ __forceinline__ Raw4<B> convert(const CP (&x)[4]) const {
+    if (s.mode == 2 || (s.mode == 1 && sizeof(CP) == 8)) {
+      double y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = __dmul_rn((double)x[i], s.ds);
+      return pack4<B, double>(y);
+    } else if (s.mode == 1) {
+      float y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = __fmul_rn((float)x[i], s.fs);  // exact: factor is 2^k
+      return pack4<B, float>(y);
+    }
+    return pack4<B, CP>(x);
+  }
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    using CP = typename Carrier<P>::type;
+    Raw4<P> in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (act[u]) in[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!act[u]) continue;
+      CP x[4];
+      unpack4(in[u], x);
+      st4(reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u], convert<B, P, CP>(x));
+    }
+  }
+
+  template <class B, class P>
+  __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
+    using CP = typename Carrier<P>::type;
+    const CP x = to_carrier(cptr<P>(g.ptr[0])[e]);
+    B out;
+    if (s.mode == 2 || (s.mode == 1 && sizeof(CP) == 8)) out = from_d<B>(__dmul_rn((double)x, s.ds));
+    else if (s.mode == 1) out = from_f<B>(__fmul_rn((float)x, s.fs));
+    else out = from_carrier<B>(x);
+    reinterpret_cast<B*>(buffer)[g.buf_off + e] = out;
+  }
+  template <class B>
+  __device__ __forceinline__ void scalar(const gp_seg_t& g, int64_t e) const {
+    switch (g.dtype0) {
+      case GP_F32: one<B, float>(g, e); break;
+      case GP_F16: one<B, __half>(g, e); break;
+      case GP_F64: one<B, double>(g, e); break;
+      default: break;
+    }
+  }
+};
+
+// ptr0[k] = (P)( (B)(scale * buffer[buf_off + k]) )
+struct UnpackOp {
+  static constexpr int kMaxUnroll = 4;
+  const void* buffer;
+  ScaleArg s;
+
+  static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    using CB = typename Carrier<B>::type;
+    using CP = typename Carrier<P>::type;
+    Raw4<B> in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (act[u]) in[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!act[u]) continue;
+      CB x[4];
+      CP g[4];
+      unpack4(in[u], x);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = gpw::mean_grad_value<B, P>(x[i], s);
+      st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
+    }
+  }
+  template <class B, class P>
+  __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
+    const auto x = to_carrier(reinterpret_cast<const B*>(buffer)[g.buf_off + e]);
+    mptr<P>(g.ptr[0])[e] = from_carrier<P>(gpw::mean_grad_value<B, P>(x, s));
+  }
+  template <class B>
+  __device__ __forceinline__ void scalar(const gp_seg_t& g, int64_t e) const {
+    switch (g.dtype0) {
+      case GP_F32: one<B, float>(g, e); break;
+      case GP_F16: one<B, __half>(g, e); break;
+      case GP_F64: one<B, double>(g, e); break;
+      default: break;
+    }
+  }
+};
+
+// ------------------------------------------------- flat (single array) ops --
+template <class B>
+__global__ void __launch_bounds__(256) scale_kernel(B* __restrict__ buf, int64_t n, ScaleArg s) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    typename Carrier<B>::type x[4];
+    unpack4(ld4(buf + 4 * i), x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = descale<B>(x[k], s);
+    st4(buf + 4 * i, pack4<B, typename Carrier<B>::type>(x));
+  }
+  // tail (< 4 elements)
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) buf[t] = from_carrier<B>(descale<B>(to_carrier(buf[t]), s));
+}
+
+__device__ __forceinline__ bool is_finite_c(float x) { return isfinite(x); }
+__device__ __forceinline__ bool is_finite_c(double x) { return isfinite(x); }
+
+template <class B>
+__global__ void __launch_bounds__(256) finite_kernel(const B* __restrict__ buf, int64_t n,
+                                                     int32_t* flag) {
+  bool bad = false;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    typename Carrier<B>::type x[4];
+    unpack4(ld4_stream(buf + 4 * i), x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bad = bad || !is_finite_c(x[k]);
+  }
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) bad = bad || !is_finite_c(to_carrier(buf[t]));
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+int flat_grid(int64_t n) {
+  int64_t g = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)gp_sm_count_cached() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int gp_pack(void* buffer, int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs,
+                       int n_segs, int64_t elem_begin, int64_t elem_end, double scale,
+                       void* stream) {
+  PackOp op;
+  op.buffer = buffer;
+  op.s = make_scale(scale);
+  return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
+                         "gp_pack");
+}
+
+extern "C" int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                               const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                               int64_t elem_end, double scale, void* stream) {
+  UnpackOp op;
+  op.buffer = buffer;
+  op.s = make_scale(scale);
+  return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
+                         "gp_unpack_scale");
+}
+
+extern "C" int gp_scale(void* buffer, int dtype, int64_t n, double scale, void* stream) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)buffer) & (gp_itemsize(dtype) == 2 ? 7 : 15)) {
+    gp_set_error("gp_scale: buffer must be aligned to 4 elements");
+    return GP_EINVAL;
+  }
+  const ScaleArg s = make_scale(scale);
+  if (s.mode == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = flat_grid(n);
+  switch (dtype) {
+    case GP_F32: scale_kernel<float><<<g, 256, 0, st>>>((float*)buffer, n, s); break;
+    case GP_F16: scale_kernel<__half><<<g, 256, 0, st>>>((__half*)buffer, n, s); break;
+    case GP_BF16: scale_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)buffer, n, s); break;
+    case GP_F64: scale_kernel<double><<<g, 256, 0, st>>>((double*)buffer, n, s); break;
+    default:
+      gp_set_error("gp_scale: unsupported dtype id %d", dtype);
+      return GP_EINVAL;
+  }
+  return gp_cuda_fail(cudaGetLastError(), "gp_scale launch");
+}
+
+extern "C" int gp_check_finite(const void* buffer, int dtype, int64_t n, int32_t* d_flag,
+                               void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = flat_grid(n);
+  switch (dtype) {
+    case GP_F32: finite_kernel<float><<<g, 256, 0, st>>>((const float*)buffer, n, d_flag); break;
+    case GP_F16: finite_kernel<__half><<<g, 256, 0, st>>>((const __half*)buffer, n, d_flag); break;
+    case GP_BF16:
+      finite_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)buffer, n, d_flag);
+      break;
+    case GP_F64: finite_kernel<double><<<g, 256, 0, st>>>((const double*)buffer, n, d_flag); break;
+    default:
+      gp_set_error("gp_check_finite: unsupported dtype id %d", dtype);
+      return GP_EINVAL;
+  }
+  return gp_cuda_fail(cudaGetLastError(), "gp_check_finite launch");
+}

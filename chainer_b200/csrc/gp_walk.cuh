@@ -1,0 +1,254 @@
+// gp_walk.cuh -- the segmented stream walker shared by the pack, unpack and
+// fused-update kernels of libgradpath (sm_100a).
+//
+// Reference being replaced: the thread-per-element kernels
+// `cupy_batched_pack_params` / `cupy_batched_unpack_params`
+// (chainermn/communicators/_memory_utility.py:289-429), which do a binary
+// search through a global-memory int32 table for EVERY element and move one
+// scalar per thread, and the per-parameter ElementwiseKernel launches of the
+// optimizers (chainer/optimizers/momentum_sgd.py:75-88, adam.py:224-332).
+//
+// Design (HBM-bound, no data reuse):
+//   * ONE launch walks the flat element space [begin, end) of the parameter
+//     list.  By default the grid is persistent (SMs x ctas_per_sm CTAs) and each
+//     CTA owns an equal contiguous slice: no wave quantisation, no tail.
+//   * The cumulative-size table (int64[n+1]) is staged into shared memory once
+//     per CTA; a warp finds the parameter of its first element with one binary
+//     search in shared memory and afterwards only walks forward.
+//   * A warp tile is 32 lanes x U vectors x 4 elements.  If every vector of the
+//     tile lies inside a 4-aligned parameter and all of them have one dtype,
+//     the tile runs in VECTOR mode: the loads of all U vectors of all arrays are
+//     issued first (8/16 B per lane, one warp instruction = 256/512 contiguous
+//     bytes), then the arithmetic, then the stores.  Otherwise (ragged sizes,
+//     mixed dtypes, the tail) the tile runs in SCALAR mode with a lane-coalesced
+//     element mapping.  Tiny parameters cost nothing extra: neighbouring lanes
+//     simply resolve to different table entries.
+#pragma once
+#include "gp_common.cuh"
+
+namespace gpw {
+
+constexpr int kMaxSmemSegs = 6143;  // (n+1) * 8 B <= 48 KB of dynamic shared memory
+constexpr int kMaxThreads = 512;
+
+struct WalkArgs {
+  const int64_t* csum;
+  const gp_seg_t* segs;
+  int n_segs;
+  int use_smem;
+  int64_t begin, end;
+  int64_t per_cta;
+};
+
+// largest j in [0, n) with cs[j] <= flat   (cs[0] <= flat < cs[n] guaranteed)
+__device__ __forceinline__ int seg_find(const int64_t* cs, int n, int64_t flat) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cs[mid] <= flat) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int seg_seek(const int64_t* cs, int n, int j, int64_t flat) {
+  while (j + 1 < n && flat >= cs[j + 1]) ++j;
+  return j;
+}
+
+// An Op supplies
+//   static int key(const gp_seg_t&)          dtype id a vector tile must agree on
+//   template <class B, class P, int U> void vec(seg[U], e[U], act[U]) const
+//   template <class B> void scalar(const gp_seg_t&, int64_t e) const
+// B = buffer element type (per launch), P = parameter element type (per tile).
+template <class Op, class B, int U>
+__global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, const Op op) {
+  extern __shared__ int64_t s_csum[];
+  const int n = a.n_segs;
+  const int64_t lo = a.begin + (int64_t)blockIdx.x * a.per_cta;
+  const int64_t hi = (lo + a.per_cta < a.end) ? lo + a.per_cta : a.end;
+  if (lo >= hi) return;
+
+  const int64_t* cs = a.csum;
+  if (a.use_smem) {
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_csum[i] = a.csum[i];
+    __syncthreads();
+    cs = s_csum;
+  }
+
+  constexpr int WT = 32 * U * 4;  // elements per warp tile
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t stride = (int64_t)(blockDim.x >> 5) * WT;
+  int64_t base = lo + (int64_t)warp * WT;
+  if (base >= hi) return;
+  int j = seg_find(cs, n, base);
+
+  for (; base < hi; base += stride) {
+    j = seg_seek(cs, n, j, base);
+
+    const gp_seg_t* sg[U];
+    int64_t e[U];
+    bool act[U];
+    bool ok = true;
+    int my_key = 0;
+    int jj = j;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t flat0 = base + (int64_t)(u * 32 + lane) * 4;
+      act[u] = flat0 < hi;
+      if (act[u]) {
+        jj = seg_seek(cs, n, jj, flat0);
+        ok = ok && (flat0 + 4 <= hi) && (flat0 + 4 <= cs[jj + 1]);
+      }
+      sg[u] = a.segs + jj;
+      e[u] = flat0 - cs[jj];
+    }
+    // lane 0 / u == 0 is always active (base < hi): its dtype is the tile's key
+    {
+      const int k0 = Op::key(*sg[0]);
+      const int key_ref = __shfl_sync(0xffffffffu, k0, 0);
+      my_key = key_ref;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (act[u]) {
+          const gp_seg_t& g = *sg[u];
+          ok = ok && (g.flags & GP_SEG_VEC_OK) && (Op::key(g) == key_ref);
+        }
+      }
+    }
+    // float64 parameters (rare: tests, scientific models) take the scalar path;
+    // keeping their vector bodies out of the kernel keeps the register count of
+    // the float32 / float16 stream low.
+    ok = __all_sync(0xffffffffu, ok && my_key != GP_F64);
+
+    if (ok) {
+      switch (my_key) {
+        case GP_F32: op.template vec<B, float, U>(sg, e, act); break;
+        case GP_F16: op.template vec<B, __half, U>(sg, e, act); break;
+        default: break;
+      }
+    } else {
+      int js = j;
+#pragma unroll 1
+      for (int k = 0; k < U * 4; ++k) {
+        const int64_t flat = base + (int64_t)k * 32 + lane;
+        if (flat < hi) {
+          js = seg_seek(cs, n, js, flat);
+          op.template scalar<B>(a.segs[js], flat - cs[js]);
+        }
+      }
+    }
+  }
+}
+
+// resident CTAs per SM of one instantiation (cached: the occupancy query is a
+// host-side calculation but not free)
+template <class Op, class B, int U>
+int resident_ctas(int threads, size_t smem) {
+  static int c_threads = -1, c_occ = 1;
+  static size_t c_smem = 0;
+  if (threads != c_threads || smem != c_smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U>, threads, smem) !=
+            cudaSuccess || occ < 1) {
+      (void)cudaGetLastError();
+      occ = 1;
+    }
+    c_threads = threads;
+    c_smem = smem;
+    c_occ = occ;
+  }
+  return c_occ;
+}
+
+template <class Op, class B, int U>
+int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st, const char* what) {
+  const GpTuning& t = g_gp_tuning;
+  const int64_t total = a.end - a.begin;
+  const int64_t cta_tile = (int64_t)threads * U * 4;
+  int64_t grid;
+  if (t.persistent) {
+    // every CTA must be resident at once, otherwise the equal slices would run
+    // in waves: cap the grid by the real occupancy of this instantiation.
+    int per_sm = resident_ctas<Op, B, U>(threads, smem);
+    if (t.ctas_per_sm > 0 && t.ctas_per_sm < per_sm) per_sm = t.ctas_per_sm;
+    const int64_t max_grid = (int64_t)gp_sm_count_cached() * per_sm;
+    grid = (total + cta_tile - 1) / cta_tile;
+    if (grid > max_grid) grid = max_grid;
+    int64_t per = (total + grid - 1) / grid;
+    per = (per + 127) & ~(int64_t)127;
+    a.per_cta = per;
+    grid = (total + per - 1) / per;
+  } else {
+    a.per_cta = cta_tile;
+    grid = (total + cta_tile - 1) / cta_tile;
+  }
+  if (grid > 0x7fffffff) {
+    gp_set_error("%s: grid too large", what);
+    return GP_EINVAL;
+  }
+  walk_kernel<Op, B, U><<<(unsigned)grid, threads, smem, st>>>(a, op);
+  return gp_cuda_fail(cudaGetLastError(), what);
+}
+
+// Choose the grid and launch.  `what` only labels error messages.
+template <class Op, class B>
+int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t begin, int64_t end,
+           const Op& op, void* stream, const char* what) {
+  if (n_segs <= 0 || end <= begin) return 0;
+  if (begin < 0 || (begin & 3)) {
+    gp_set_error("%s: elem_begin (%lld) must be a non-negative multiple of 4", what,
+                 (long long)begin);
+    return GP_EINVAL;
+  }
+  const GpTuning& t = g_gp_tuning;
+  int threads = t.threads;
+  if (threads < 32) threads = 32;
+  if (threads > kMaxThreads) threads = kMaxThreads;
+  threads &= ~31;
+  int U = t.unroll >= 4 ? 4 : (t.unroll >= 2 ? 2 : 1);
+  if (sizeof(B) == 8 && U > 2) U = 2;
+  if (U > Op::kMaxUnroll) U = Op::kMaxUnroll;
+
+  WalkArgs a;
+  a.csum = d_csum;
+  a.segs = d_segs;
+  a.n_segs = n_segs;
+  a.use_smem = n_segs <= kMaxSmemSegs;
+  a.begin = begin;
+  a.end = end;
+  a.per_cta = 0;
+  const size_t smem = a.use_smem ? (size_t)(n_segs + 1) * sizeof(int64_t) : 0;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (U) {
+    case 4: return launch_u<Op, B, 4>(a, op, threads, smem, st, what);
+    case 2: return launch_u<Op, B, 2>(a, op, threads, smem, st, what);
+    default: return launch_u<Op, B, 1>(a, op, threads, smem, st, what);
+  }
+}
+
+// dispatch on the runtime buffer dtype
+template <class Op>
+int launch_buf(int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs,
+               int64_t begin, int64_t end, const Op& op, void* stream, const char* what) {
+  switch (buf_dtype) {
+    case GP_F32: return launch<Op, float>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
+    case GP_F16: return launch<Op, __half>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
+    case GP_BF16: return launch<Op, __nv_bfloat16>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
+    case GP_F64: return launch<Op, double>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
+    default:
+      gp_set_error("%s: unsupported buffer dtype id %d", what, buf_dtype);
+      return GP_EINVAL;
+  }
+}
+
+// value of the packed buffer (type B, as carrier) -> mean gradient in the
+// parameter's type P (as carrier): descale, round to B (the reference scales the
+// buffer in place), then cast to P (unpack kernel, _memory_utility.py:392-425).
+template <class B, class P>
+__device__ __forceinline__ typename Carrier<P>::type mean_grad_value(
+    typename Carrier<B>::type x, const ScaleArg& s) {
+  return round_through<P>(descale<B>(x, s));
+}
+
+}  // namespace gpw

@@ -1,0 +1,255 @@
+/*
+ * gradpath.h -- C-ABI of libgradpath.so: the B200 (sm_100a) implementation of
+ * ChainerMN's data-parallel gradient path.
+ *
+ * Every entry point replaces one piece of the reference's `pure_nccl` path; the
+ * reference location is cited beside each declaration (paths are relative to the
+ * chainer/chainer v7.8.1 tree).  The reference binds its kernels through CuPy's
+ * NVRTC JIT (`chainer.cuda.raw` / `chainer.cuda.elementwise`) and NCCL through
+ * `cupy.cuda.nccl`; this library is what a maintainer binds instead, with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, doubles.  No torch / cupy types.
+ *   - every function returns 0 on success, a negative code on failure:
+ *       -(1000 + cudaError_t)  for CUDA runtime failures
+ *       -(2000 + ncclResult_t) for NCCL failures
+ *       GP_EINVAL / GP_ENOSYS  for bad arguments / missing NCCL symbols
+ *     gp_last_error() returns a thread-local human readable message.
+ *   - the caller owns every data buffer.  The library owns only the handles it
+ *     creates (gp_*_create) and frees them in gp_*_destroy.
+ *   - all kernels are asynchronous on the `stream` argument (a cudaStream_t
+ *     passed as void*; NULL is the legacy default stream, which is what
+ *     `chainer.cuda.Stream.null.ptr` is in the reference).
+ *   - dtype ids are NCCL's: 6 = float16, 7 = float32, 8 = float64, 9 = bfloat16
+ *     (reference: chainermn/nccl.py:1-14, _communication_utility.py:177-186;
+ *      bfloat16 is an extension with no reference counterpart).
+ */
+#ifndef GRADPATH_H_
+#define GRADPATH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+#define GP_F16 6
+#define GP_F32 7
+#define GP_F64 8
+#define GP_BF16 9
+
+#define GP_EINVAL (-22)
+#define GP_ENOSYS (-38)
+
+/* flags of gp_seg_t.flags */
+#define GP_SEG_VEC_OK 1u /* all pointers 4-element aligned and csum/buf_off % 4 == 0 */
+
+/* flags of gp_unpack_adam */
+#define GP_ADAM_AMSGRAD 1
+#define GP_ADAM_ADABOUND 2
+
+/*
+ * One entry of the device-side segment table: one parameter of the model.
+ * Replaces the three device arrays of `ParamsData`
+ * (chainermn/communicators/_memory_utility.py:31-62: dptr int64[n],
+ * dtype int32[n], size_csum int32[n+1]).  The cumulative sizes live in a
+ * separate int64[n+1] array (`csum`) so that it can be staged in shared
+ * memory compactly; int64 instead of the reference's int32 so that buffers
+ * beyond 2^31 elements do not overflow.
+ *
+ *   ptr[0]  the array that is packed / unpacked (param.grad or param.data);
+ *           in the fused update kernels: where the mean gradient is written
+ *           back (may be 0 when write_grad == 0)
+ *   ptr[1]  param.data                         (fused update only)
+ *   ptr[2]  state 'v' (MomentumSGD) / 'm' (Adam)
+ *   ptr[3]  state 'v' (Adam)
+ *   ptr[4]  state 'vhat' (AMSGrad)
+ *   buf_off element offset of this parameter inside the packed buffer
+ *   dtype0  dtype id of ptr[0]; dtype1 dtype id of ptr[1..4]
+ */
+typedef struct gp_seg_t {
+  uint64_t ptr[5];
+  int64_t buf_off;
+  int32_t dtype0;
+  int32_t dtype1;
+  uint32_t flags;
+  uint32_t reserved;
+} gp_seg_t; /* 64 bytes */
+
+/* ---------------------------------------------------------------- errors -- */
+const char* gp_last_error(void);
+int gp_abi_version(void);
+
+/* ------------------------------------------------------- device / memory -- */
+/* Plumbing the reference gets from CuPy (cupy.cuda.alloc, Stream, Event,
+ * MemoryPointer.copy_from_device_async: _memory_utility.py:65-151). */
+int gp_device_count(int* count);
+int gp_set_device(int device);
+int gp_get_device(int* device);
+int gp_device_synchronize(void);
+int gp_device_sm_count(int* count);
+int gp_malloc(void** ptr, size_t nbytes);
+int gp_free(void* ptr);
+int gp_malloc_host(void** ptr, size_t nbytes); /* pinned */
+int gp_free_host(void* ptr);
+/* kind: 0 = host->device, 1 = device->host, 2 = device->device */
+int gp_memcpy_async(void* dst, const void* src, size_t nbytes, int kind, void* stream);
+int gp_memset_async(void* dst, int value, size_t nbytes, void* stream);
+int gp_stream_create(void** stream, int non_blocking);
+int gp_stream_destroy(void* stream);
+int gp_stream_synchronize(void* stream);
+int gp_stream_wait_event(void* stream, void* event);
+int gp_event_create(void** event, int enable_timing);
+int gp_event_destroy(void* event);
+int gp_event_record(void* event, void* stream);
+int gp_event_synchronize(void* event);
+int gp_event_elapsed_ms(float* ms, void* start, void* stop);
+
+/* Upload of a host table (csum + segments) without a host sync.  The handle
+ * owns a device arena and a ring of pinned staging slots; replaces the three
+ * synchronous `cupy.asarray` calls of ParamsData (_memory_utility.py:59-61).
+ * `*device_ptr` receives the device address of the uploaded copy (256-byte
+ * aligned, valid until the 4th following upload on the same handle). */
+int gp_table_create(void** table);
+int gp_table_destroy(void* table);
+int gp_table_upload(void* table, const void* host_src, size_t nbytes, void* stream,
+                    void** device_ptr);
+
+/* ------------------------------------------------------ gradient kernels -- */
+/*
+ * gp_pack: gather + cast (+ optional pre-scale) of n_segs arrays into the
+ * contiguous packed buffer.  buffer[seg.buf_off + k] = (buf_dtype)(scale * ptr0[k]).
+ * Replaces kernel `cupy_batched_pack_params` (_memory_utility.py:289-358,
+ * launched at :253-268) and, with scale != 1, folds `div_by_size`
+ * (pure_nccl_communicator.py:183-189) into the pack.
+ *
+ * d_csum[n_segs + 1] (int64, device) are the cumulative element counts in this
+ * call's work space; d_segs[n_segs] the segment entries.  Only work elements in
+ * [elem_begin, elem_end) are processed (bucketing); pass 0 and d_csum[n_segs]
+ * for everything.
+ */
+int gp_pack(void* buffer, int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs,
+            int n_segs, int64_t elem_begin, int64_t elem_end, double scale, void* stream);
+
+/*
+ * gp_unpack_scale: ptr0[k] = (dtype0)( (buf_dtype)(scale * buffer[buf_off + k]) ).
+ * Replaces `div_by_size` + kernel `cupy_batched_unpack_params`
+ * (pure_nccl_communicator.py:183-189, _memory_utility.py:361-429).  The
+ * intermediate rounding to buf_dtype reproduces the reference, which scales the
+ * receive buffer in place before unpacking it.  scale == 1.0 is a pure unpack
+ * (used by bcast_data, pure_nccl_communicator.py:82-99).
+ */
+int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                    const gp_seg_t* d_segs, int n_segs, int64_t elem_begin, int64_t elem_end,
+                    double scale, void* stream);
+
+/*
+ * gp_unpack_momentum_sgd: fused unpack + descale + MomentumSGD update.
+ *   g = (dtype0)((buf_dtype)(scale * buffer[buf_off + k]))
+ *   v = momentum * v - lr * g ;  param += v        (arithmetic in dtype1)
+ *   if write_grad: ptr0[k] = g
+ * Replaces unpack (above) + one `momentum_sgd` ElementwiseKernel launch per
+ * parameter (chainer/optimizers/momentum_sgd.py:75-88).  Each gradient element
+ * is read from HBM exactly once.  No fused multiply-add contraction is used:
+ * the result is bit-identical to update_core_cpu (momentum_sgd.py:61-73).
+ */
+int gp_unpack_momentum_sgd(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                           const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                           int64_t elem_end, double scale, double lr, double momentum,
+                           int write_grad, void* stream);
+
+/*
+ * gp_unpack_adam: fused unpack + descale + Adam / AdamW / AMSGrad / AdaBound.
+ *   m += (1-beta1)(g-m); v += (1-beta2)(g*g-v); [vhat = max(vhat, v)]
+ *   param -= eta * (alpha_t * m / (sqrt(v) + eps) + weight_decay_rate * param)
+ * with the exact operation order of the `adam` / `amsgrad` / `adabound` /
+ * `amsbound` ElementwiseKernels (chainer/optimizers/adam.py:237-332);
+ * intermediate type float for float16/float32 parameters, double for float64
+ * (adam.py:57-63).  alpha_t (adam.py:47-54) and the AdaBound bounds
+ * (adam.py:346-358) are computed by the caller in double.
+ */
+int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                   const gp_seg_t* d_segs, int n_segs, int64_t elem_begin, int64_t elem_end,
+                   double scale, double alpha_t, double one_minus_beta1,
+                   double one_minus_beta2, double eps, double eta, double weight_decay_rate,
+                   double lower, double upper, int adam_flags, int write_grad, void* stream);
+
+/* gp_scale: buffer[k] = (dtype)(buffer[k] * scale), in place.  Replaces the
+ * `div_by_size` ElementwiseKernel (pure_nccl_communicator.py:183-189) where it
+ * is used stand-alone (MNBN statistics, functions/batch_normalization.py:57-60). */
+int gp_scale(void* buffer, int dtype, int64_t n_elems, double scale, void* stream);
+
+/* gp_check_finite: *d_flag |= 1 if any element is NaN/Inf.  Replaces
+ * `_ensure_all_finite` (mpi_communicator_base.py:730-733) in debug mode. */
+int gp_check_finite(const void* buffer, int dtype, int64_t n_elems, int32_t* d_flag,
+                    void* stream);
+
+/* ------------------------------------------- batch-normalisation statistics -- */
+/*
+ * gp_bn_fwd_stats: one pass over x[N, C, HW] (C-contiguous, x_dtype) producing
+ * out[0:C] = mean over (N, HW), out[C:2C] = mean of squares, in out_dtype.
+ * Replaces `x.mean(axis)`, `xp.square(x).mean(axis)` of
+ * _NcclImpl.get_mean_and_var (chainermn/functions/batch_normalization.py:53-56),
+ * which reads x twice and materialises square(x).
+ * workspace: device scratch of gp_bn_workspace_bytes(C) bytes, zero-initialised
+ * once by the caller (the kernel leaves it zeroed again).
+ */
+size_t gp_bn_workspace_bytes(int64_t C);
+int gp_bn_fwd_stats(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW, void* out,
+                    int out_dtype, void* workspace, void* stream);
+/*
+ * gp_bn_bwd_stats: out[0:C] = sum(gy), out[C:2C] = sum(gy * x_hat) over (N, HW).
+ * Replaces `gy.sum(axis)`, `(gy * x_hat).sum(axis)` of
+ * _NcclImpl.get_ggamma_and_gbeta (functions/batch_normalization.py:79-82).
+ * If mean/inv_std are non-NULL, `xhat_or_x` holds x and x_hat is formed on the
+ * fly as (x - mean[c]) * inv_std[c] (chainer/functions/normalization/
+ * batch_normalization.py:107-108, `_x_hat`).
+ */
+int gp_bn_bwd_stats(const void* gy, int gy_dtype, const void* xhat_or_x, int x_dtype,
+                    const void* mean, const void* inv_std, int stat_dtype, int64_t N, int64_t C,
+                    int64_t HW, void* out, int out_dtype, void* workspace, void* stream);
+/* var = sqmean - mean^2 in place on a [mean | sqmean] buffer after the
+ * allreduce (functions/batch_normalization.py:65-67), fused with the 1/size
+ * scale: buf[k] *= scale first.  out_var[C] may alias buf + C. */
+int gp_bn_finish_mean_var(void* buf, int dtype, int64_t C, double scale, void* out_var,
+                          void* stream);
+
+/* ------------------------------------------------------------------ NCCL -- */
+/* Thin wrappers over libnccl.so.2, resolved with dlopen at gp_nccl_load time;
+ * replaces `cupy.cuda.nccl` (chainermn/nccl.py:1-14) and
+ * `init_nccl_comm` (_communication_utility.py:69-76). */
+#define GP_NCCL_UNIQUE_ID_BYTES 128
+#define GP_NCCL_SUM 0
+int gp_nccl_load(const char* libnccl_path); /* NULL: "libnccl.so.2" from the loader path */
+int gp_nccl_version(int* version);
+int gp_nccl_get_unique_id(char* id128);
+int gp_nccl_comm_init_rank(void** comm, int n_ranks, const char* id128, int rank);
+int gp_nccl_comm_destroy(void* comm);
+int gp_nccl_allreduce(void* comm, const void* sendbuf, void* recvbuf, int64_t count, int dtype,
+                      int op, void* stream);
+int gp_nccl_bcast(void* comm, void* buffer, int64_t count, int dtype, int root, void* stream);
+int gp_nccl_reduce(void* comm, const void* sendbuf, void* recvbuf, int64_t count, int dtype,
+                   int op, int root, void* stream);
+int gp_nccl_group_start(void);
+int gp_nccl_group_end(void);
+/* ncclMemAlloc / ncclCommRegister: user-buffer registration makes the packed
+ * buffer eligible for NVLS (in-switch reduction) on NVSwitch systems. */
+int gp_nccl_mem_alloc(void** ptr, size_t nbytes);
+int gp_nccl_mem_free(void* ptr);
+int gp_nccl_comm_register(void* comm, void* buffer, size_t nbytes, void** handle);
+int gp_nccl_comm_deregister(void* comm, void* handle);
+
+/* ---------------------------------------------------------------- tuning -- */
+/* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking
+ * sweeps; defaults are the tuned values recorded in DESIGN.md. */
+int gp_set_tuning(const char* key, int value);
+int gp_get_tuning(const char* key, int* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRADPATH_H_ */
