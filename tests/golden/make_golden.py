@@ -1,0 +1,253 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (chainer/chainer v7.8.1, imported from /root/reference through
+`_ref_shims`) on seeded inputs.
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  layouts.json          sorted(model.namedparams()) of the example models
+  momentum_sgd.npz      chainer.optimizers.MomentumSGD, 3 steps, f16/f32/f64
+  adam.npz              chainer.optimizers.Adam (+AdamW, AMSGrad, AdaBound, AMSBound)
+  naive_mean_grad.npz   chainermn NaiveCommunicator.multi_node_mean_grad, 2 and 3 ranks
+  mnbn.npz              MultiNodeBatchNormalization (_MpiImpl) forward/backward, 2 ranks
+The reference tree is not available on the GPU box, hence fixtures.
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_shims  # noqa: E402
+
+chainer, chainermn = _ref_shims.import_reference()
+import chainer.functions as F  # noqa: E402
+import chainer.links as L  # noqa: E402
+from chainer import optimizers  # noqa: E402
+
+EX = os.path.join(_ref_shims.REFERENCE_ROOT, 'examples', 'chainermn')
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _layout(model):
+    return [[name, list(p.shape), str(p.dtype)] for name, p in sorted(model.namedparams())]
+
+
+def make_layouts():
+    out = {}
+    resnet = _load(os.path.join(EX, 'imagenet', 'models', 'resnet50.py'), 'ref_resnet50')
+    out['resnet50'] = _layout(resnet.ResNet50())
+    mnist = _load(os.path.join(EX, 'mnist', 'train_mnist.py'), 'ref_train_mnist')
+    mlp = mnist.MLP(1000, 10)
+    mlp(np.zeros((1, 784), dtype=np.float32))          # resolve the lazy input sizes
+    out['mnist_mlp'] = _layout(mlp)
+    # seq2seq.py imports nltk (absent) and `europal`: stub / path them for the import only
+    nltk = types.ModuleType('nltk')
+    tr = types.ModuleType('nltk.translate')
+    tr.bleu_score = types.ModuleType('nltk.translate.bleu_score')
+    nltk.translate = tr
+    sys.modules.update({'nltk': nltk, 'nltk.translate': tr,
+                        'nltk.translate.bleu_score': tr.bleu_score,
+                        'progressbar': types.ModuleType('progressbar')})
+    sys.path.insert(0, os.path.join(EX, 'seq2seq'))
+    s2s = _load(os.path.join(EX, 'seq2seq', 'seq2seq.py'), 'ref_seq2seq')
+    model = s2s.Seq2seq(3, 40000, 40000, 1024)
+    out['seq2seq'] = _layout(model)
+    with open(os.path.join(HERE, 'layouts.json'), 'w') as f:
+        json.dump(out, f, indent=0)
+    for k, v in out.items():
+        print('layout', k, len(v), sum(int(np.prod(s)) for _, s, _ in v))
+
+
+class _Net(chainer.Chain):
+    """Parameters of the given shapes, registered as a, b, c, ..."""
+
+    def __init__(self, shapes, dtype, rng):
+        super(_Net, self).__init__()
+        with self.init_scope():
+            for i, shape in enumerate(shapes):
+                init = np.asarray(rng.standard_normal(shape) * 0.05).astype(dtype).reshape(shape)
+                setattr(self, 'p%02d' % i, chainer.Parameter(init))
+
+
+SHAPES = [(2, 3), (), (1, 0, 2), (257,), (130,), (8, 3, 3, 3)]
+
+
+def _run_optimizer(make_opt, dtype, n_steps, seed, grad_scale=1e-2):
+    rng = np.random.default_rng(seed)
+    net = _Net(SHAPES, dtype, rng)
+    opt = make_opt()
+    opt.setup(net)
+    rec = {}
+    names = [n for n, _ in sorted(net.namedparams())]
+    for n, p in sorted(net.namedparams()):
+        rec['init' + n] = p.data.copy()
+    for step in range(n_steps):
+        for n, p in sorted(net.namedparams()):
+            g = np.asarray(rng.standard_normal(p.shape) * grad_scale).astype(dtype).reshape(p.shape)
+            p.grad = g
+            rec['grad%d%s' % (step, n)] = g.copy()
+        opt.update()
+        for n, p in sorted(net.namedparams()):
+            rec['param%d%s' % (step, n)] = p.data.copy()
+            for k, s in p.update_rule.state.items():
+                rec['state_%s%d%s' % (k, step, n)] = np.array(s, copy=True)
+    return names, rec
+
+
+def make_momentum_sgd():
+    out = {}
+    for dtype in ('float32', 'float16', 'float64'):
+        names, rec = _run_optimizer(lambda: optimizers.MomentumSGD(lr=0.01, momentum=0.9),
+                                    np.dtype(dtype), 3, 11)
+        for k, v in rec.items():
+            out['%s|%s' % (dtype, k)] = v
+    np.savez_compressed(os.path.join(HERE, 'momentum_sgd.npz'), **out)
+    print('momentum_sgd', len(out))
+
+
+ADAM_VARIANTS = {
+    'adam': dict(),
+    'adamw': dict(eta=0.5, weight_decay_rate=0.1),
+    'amsgrad': dict(amsgrad=True),
+    'adabound': dict(adabound=True),
+    'amsbound': dict(amsgrad=True, adabound=True),
+}
+
+
+def make_adam():
+    out = {}
+    for variant, kw in ADAM_VARIANTS.items():
+        for dtype in ('float32', 'float16', 'float64'):
+            # float16: gradients of O(1) so that v = (1-beta2) g^2 stays a normal half
+            # number (with 1e-2 it underflows in the reference's float16 state and
+            # its CPU and GPU code paths legitimately diverge)
+            names, rec = _run_optimizer(lambda: optimizers.Adam(**kw), np.dtype(dtype), 3, 13,
+                                        grad_scale=0.5 if dtype == 'float16' else 1e-2)
+            for k, v in rec.items():
+                out['%s|%s|%s' % (variant, dtype, k)] = v
+    # the reference's own known-answer test: tests/chainer_tests/optimizers_tests/
+    # test_optimizers.py:278-310 (TestAdamW) x=1, g=1, eta=.5, wd=.1 -> 0.9495
+    link = chainer.Link(x=(1,))
+    link.x.data.fill(1)
+    link.x.grad = np.ones_like(link.x.data)
+    opt = optimizers.Adam(eta=0.5, weight_decay_rate=0.1)
+    opt.setup(link)
+    opt.update()
+    out['kat|adamw'] = link.x.data.copy()
+    np.savez_compressed(os.path.join(HERE, 'adam.npz'), **out)
+    print('adam', len(out), 'AdamW KAT', out['kat|adamw'])
+
+
+def make_naive_mean_grad():
+    """NaiveCommunicator.multi_node_mean_grad (naive_communicator.py:10-17 ->
+    mpi_communicator_base.py:735-778) on `size` ranks, rank-dependent grads,
+    including a None grad with zero_fill and an uninitialised parameter."""
+    from chainermn.communicators.naive_communicator import NaiveCommunicator
+    out = {}
+    for size in (2, 3):
+        for dtype in ('float32', 'float16', 'float64'):
+            def fn(mpi_comm, rank, dtype=dtype):
+                comm = NaiveCommunicator(mpi_comm)
+                rng = np.random.default_rng(7)
+                net = _Net([(2, 3), (5,), (3, 4), (0,), (33,)], np.dtype(dtype), rng)
+                with net.init_scope():
+                    net.lazy = L.Linear(None, 5)              # W uninitialised: skipped
+                grng = np.random.default_rng(1000 + rank)
+                grads = {}
+                for n, p in sorted(net.namedparams()):
+                    if p.data is None:
+                        continue
+                    g = np.asarray(grng.standard_normal(p.shape) * 1e-2).astype(p.dtype).reshape(p.shape)
+                    if n == '/p01' and rank % 2 == 1:
+                        p.grad = None                          # zero_fill case
+                        g = np.zeros(p.shape, dtype=p.dtype)
+                    else:
+                        p.grad = g.copy()
+                    grads[n] = g
+                comm.multi_node_mean_grad(net, zero_fill=True)
+                res = {n: p.grad.copy() for n, p in sorted(net.namedparams())
+                       if p.data is not None}
+                return grads, res
+            results = _ref_shims.run_ranks(size, fn)
+            for r, (grads, res) in enumerate(results):
+                for n, g in grads.items():
+                    out['%d|%s|in|%d|%s' % (size, dtype, r, n)] = g
+                for n, g in res.items():
+                    out['%d|%s|out|%d|%s' % (size, dtype, r, n)] = g
+    np.savez_compressed(os.path.join(HERE, 'naive_mean_grad.npz'), **out)
+    print('naive_mean_grad', len(out))
+
+
+def make_mnbn():
+    """MultiNodeBatchNormalization with the MPI backend (`_MpiImpl`,
+    chainermn/functions/batch_normalization.py:7-32) on 2 ranks: forward output,
+    running statistics, and gradients; plus the single-process BatchNormalization
+    on the concatenated batch (the equivalence the reference tests,
+    tests/chainermn_tests/links_tests/test_batch_normalization.py:54-186)."""
+    from chainermn.communicators.naive_communicator import NaiveCommunicator
+    from chainermn.links import MultiNodeBatchNormalization
+    out = {}
+    size, nb, C, H, W = 2, 4, 6, 5, 3
+    rng = np.random.default_rng(71)
+    x_all = rng.standard_normal((size * nb, C, H, W)).astype(np.float32)
+    gy_all = (rng.standard_normal((size * nb, C, H, W)) * 1e-1).astype(np.float32)
+    gamma0 = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    beta0 = rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    out['x'], out['gy'], out['gamma'], out['beta'] = x_all, gy_all, gamma0, beta0
+
+    def fn(mpi_comm, rank):
+        comm = NaiveCommunicator(mpi_comm)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            bn = MultiNodeBatchNormalization(C, comm, communication_backend='mpi')
+        bn.gamma.data[...] = gamma0
+        bn.beta.data[...] = beta0
+        x = chainer.Variable(x_all[rank * nb:(rank + 1) * nb].copy())
+        with chainer.using_config('train', True):
+            y = bn(x)
+        y.grad = gy_all[rank * nb:(rank + 1) * nb].copy()
+        bn.cleargrads()
+        y.backward()
+        return dict(y=y.data.copy(), gx=x.grad.copy(), ggamma=bn.gamma.grad.copy(),
+                    gbeta=bn.beta.grad.copy(), avg_mean=bn.avg_mean.copy(),
+                    avg_var=bn.avg_var.copy())
+    for r, res in enumerate(_ref_shims.run_ranks(size, fn)):
+        for k, v in res.items():
+            out['mn|%d|%s' % (r, k)] = v
+    # single process, whole batch, stock BatchNormalization
+    bn = L.BatchNormalization(C)
+    bn.gamma.data[...] = gamma0
+    bn.beta.data[...] = beta0
+    x = chainer.Variable(x_all.copy())
+    with chainer.using_config('train', True):
+        y = bn(x)
+    y.grad = gy_all.copy()
+    bn.cleargrads()
+    y.backward()
+    out['single|y'] = y.data.copy()
+    out['single|gx'] = x.grad.copy()
+    out['single|ggamma'] = bn.gamma.grad.copy()
+    out['single|gbeta'] = bn.beta.grad.copy()
+    np.savez_compressed(os.path.join(HERE, 'mnbn.npz'), **out)
+    print('mnbn', len(out))
+
+
+if __name__ == '__main__':
+    make_layouts()
+    make_momentum_sgd()
+    make_adam()
+    make_naive_mean_grad()
+    make_mnbn()
