@@ -1,0 +1,477 @@
+"""PureNcclCommunicator: the B200 implementation of the reference class of the
+same name (``chainermn/communicators/pure_nccl_communicator.py:13-193``) on top
+of ``MpiCommunicatorBase`` (``mpi_communicator_base.py:99-815``).
+
+Same public surface and error behaviour: ``__init__(mpi_comm)``, lazy
+``_init_comms`` (the NCCL communicator binds to the CUDA device that is current
+when it is first needed, ``:30-34``), ``finalize``, ``set_config`` /
+``get_config`` (``allreduce_grad_dtype``, ``batched_copy``), ``bcast_data``,
+``multi_node_mean_grad``, ``_multi_node_mean_grad_async(model, zero_fill,
+stream)``, ``_multi_node_mean_nccl(sendbuf, recvbuf, n_elems, dtype, stream)``,
+``nccl_comm.allReduce(...)`` positional arguments.
+
+What changes underneath (none of it observable through that surface):
+
+* pack is ONE multi-tensor launch with the table staged in shared memory
+  (gp_pack) and a single asynchronous table upload;
+* the allreduce runs IN PLACE on the packed buffer, split into buckets that
+  are issued on a side stream as soon as each bucket is packed, so that the
+  allreduce of bucket i overlaps the pack of bucket i+1 and the unpack/update of
+  bucket i-1;
+* ``div_by_size`` and unpack are one kernel (gp_unpack_scale), with the
+  reference's rounding sequence (scale in double, round to the buffer dtype,
+  cast to the gradient dtype);
+* ``multi_node_mean_grad_and_update`` additionally fuses the optimizer update
+  (MomentumSGD / Adam) into that kernel.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+
+from chainer_b200 import _lib
+from chainer_b200 import config
+from chainer_b200 import device as _dev
+from chainer_b200 import nccl
+from chainer_b200.communicators import _communication_utility
+from chainer_b200.communicators import _memory_utility
+from chainer_b200.communicators import mpi_communicator_base
+
+
+class _SelfNcclComm(object):
+    """``nccl_comm`` of a single-process world: SUM over one rank is a copy.
+    Keeps the ``allReduce`` / ``bcast`` call surface (tests spy on it)."""
+
+    size = 1
+    rank = 0
+
+    def allReduce(self, sendbuf, recvbuf, count, datatype, op, stream):
+        if sendbuf != recvbuf and count > 0:
+            itemsize = 8 if datatype == nccl.NCCL_FLOAT64 else (4 if datatype == nccl.NCCL_FLOAT32 else 2)
+            _lib.get().gp_memcpy_async(recvbuf, sendbuf, count * itemsize, 2, stream)
+
+    def bcast(self, buff, count, datatype, root, stream):
+        pass
+
+    def reduce(self, sendbuf, recvbuf, count, datatype, op, root, stream):
+        self.allReduce(sendbuf, recvbuf, count, datatype, op, stream)
+
+    def destroy(self):
+        pass
+
+
+class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
+
+    def __init__(self, mpi_comm):
+        super(PureNcclCommunicator, self).__init__(mpi_comm)
+        _lib.get()  # fail loudly now if libgradpath.so is missing
+        if self.size > 1:
+            try:
+                version = nccl.get_version()
+            except Exception as e:
+                raise RuntimeError(
+                    'PureNcclCommunicator requires NCCL 2.0+, '
+                    'but NCCL is not available. ({})'.format(e))
+            if version < 2000:
+                raise RuntimeError(
+                    'PureNcclCommunicator requires NCCL 2.0+, '
+                    'but found {}.'.format(version))
+            if version < 2302:
+                warnings.warn('NCCL 2.2 and older versions are deprecated.',
+                              DeprecationWarning)
+
+        # NCCL communicators bind to the current CUDA device: delay the
+        # initialisation until the user has selected it
+        # (pure_nccl_communicator.py:30-34).
+        self.nccl_comm = None
+
+        self.gpu_tmp_buffer = _memory_utility.DeviceMemory()
+        self.gpu_buffer_a = _memory_utility.DeviceMemory()
+        self.gpu_buffer_b = _memory_utility.DeviceMemory()
+
+        with self.config_scope():
+            self.allreduce_grad_dtype = None
+        self.grad_dtype_to_allreduce_dtype_kernel = None
+        self.allreduce_dtype_to_grad_dtype_kernel = None
+        self.params_data = None
+
+        # B200 additions (not configs of the reference)
+        self.bucket_bytes = 32 << 20     # allreduce bucket size when size > 1
+        self.write_grad = True           # fused update keeps param.grad observable
+        self._comm_stream = None
+        self._events = []
+        self._table_grad = None
+        self._table_data = None
+        self._table_fused = None
+        self._finite_flag = None
+
+    # ------------------------------------------------------------ lifecycle --
+    def finalize(self):
+        super(PureNcclCommunicator, self).finalize()
+        if self.nccl_comm is not None:
+            _dev.Stream.null.synchronize()
+            if self._comm_stream is not None:
+                self._comm_stream.synchronize()
+            self.mpi_comm.barrier()
+            self.nccl_comm.destroy()
+            self.nccl_comm = None
+
+    def _init_comms(self):
+        if self.nccl_comm is not None:
+            return
+        if self.size == 1:
+            self.nccl_comm = _SelfNcclComm()
+        else:
+            self.nccl_comm = _communication_utility.init_nccl_comm(self.mpi_comm)
+
+    def set_config(self, name, value=True, **kwargs):
+        if name == 'allreduce_grad_dtype':
+            if value is not None:
+                if isinstance(value, str) and value == 'bfloat16':
+                    allreduce_grad_dtype = 'bfloat16'       # extension: no NumPy dtype exists
+                else:
+                    allreduce_grad_dtype = np.dtype(value)
+                    if allreduce_grad_dtype.kind != 'f':
+                        raise ValueError(
+                            'allreduce_grad_dtype must be'
+                            'numpy.float16, numpy.float32,'
+                            'numpy.float64, or None.')
+            else:
+                allreduce_grad_dtype = None
+
+            with self.config_scope():
+                self.allreduce_grad_dtype = allreduce_grad_dtype
+        else:
+            super(PureNcclCommunicator, self).set_config(name, value, **kwargs)
+
+    def get_config(self, name=None):
+        if name == 'allreduce_grad_dtype':
+            return self.allreduce_grad_dtype
+        else:
+            return super(PureNcclCommunicator, self).get_config(name)
+
+    # ---------------------------------------------------------- bcast_data --
+    def bcast_data(self, model):
+        """``pure_nccl_communicator.py:82-99`` -- same layout and transfer dtype
+        (``chainer.get_dtype()``); batched pack / unpack instead of one cast +
+        memcpy per parameter."""
+        self._init_comms()
+        params = _memory_utility.extract_params_set_data(model)
+        data_dtype = config.get_dtype()
+        n_elems = sum(_dev.array_size(param.data) for param in params)
+        data_grad_n_bytes = data_dtype.itemsize * n_elems
+        if self.gpu_tmp_buffer.size != data_grad_n_bytes:
+            self.gpu_tmp_buffer.assign(data_grad_n_bytes)
+        stream = _dev.Stream.null
+        if n_elems == 0:
+            return
+        if self._table_data is None:
+            self._table_data = _memory_utility.DeviceTable()
+        pd = _memory_utility.ParamsData(params, 'data', False, stream=stream,
+                                        table=self._table_data)
+        _memory_utility._batched_pack_params(pd, self.gpu_tmp_buffer, data_dtype, stream)
+        self.nccl_comm.bcast(self.gpu_tmp_buffer.ptr(), n_elems,
+                             _communication_utility._get_nccl_type_id(data_dtype),
+                             0, stream.ptr)
+        _memory_utility._batched_unpack_params(pd, self.gpu_tmp_buffer, data_dtype, stream)
+
+    # ------------------------------------------------- multi_node_mean_grad --
+    def multi_node_mean_grad(self, model, zero_fill=False):
+        stream = _dev.Stream.null
+        self._multi_node_mean_grad_async(model, zero_fill, stream)
+
+    def _allreduce_dtype(self):
+        # NOTE: explicit `is None` as in the reference (:111-114)
+        if self.allreduce_grad_dtype is not None:
+            return self.allreduce_grad_dtype
+        return config.get_dtype()
+
+    def _multi_node_mean_grad_async(self, model, zero_fill, stream):
+        """``pure_nccl_communicator.py:105-139``."""
+        self._init_comms()
+        params = _memory_utility.extract_params_set_grad(model, zero_fill)
+        allreduce_grad_dtype = self._allreduce_dtype()
+        assert allreduce_grad_dtype is not None
+
+        if self._table_grad is None:
+            self._table_grad = _memory_utility.DeviceTable()
+        # zero_fill creates missing gradients here (ParamsData, :40-42)
+        pd = _memory_utility.ParamsData(params, 'grad', zero_fill, stream=stream,
+                                        table=self._table_grad)
+        n_elems = pd.n_elems
+        needs_sync = self._prepare_allreduce_pack_buffer(allreduce_grad_dtype, n_elems)
+        if stream != _dev.Stream.null and needs_sync:
+            _dev.Stream.null.synchronize()
+        if n_elems == 0:
+            return
+        self.params_data = None
+
+        def unpack(begin, end):
+            _memory_utility._batched_unpack_params(
+                pd, self.gpu_buffer_a, allreduce_grad_dtype, stream,
+                scale=1.0 / self.size, elem_begin=begin, elem_end=end)
+
+        self._pipeline(pd, allreduce_grad_dtype, stream, unpack)
+
+    def _prepare_allreduce_pack_buffer(self, allreduce_grad_dtype, n_elems):
+        """``:141-152``.  Only buffer A is needed: the allreduce is in place."""
+        allreduce_grad_n_bytes = _dev.dtype_itemsize(allreduce_grad_dtype) * n_elems
+        needs_sync = False
+        if self.gpu_buffer_a.size != allreduce_grad_n_bytes:
+            self.gpu_buffer_a.assign(allreduce_grad_n_bytes)
+            needs_sync = True
+        return needs_sync
+
+    def _bucket_bounds(self, n_elems, itemsize):
+        if self.size == 1 or self.bucket_bytes <= 0:
+            return [0, n_elems]
+        per = max(self.bucket_bytes // itemsize, 1024) // 1024 * 1024
+        bounds = list(range(0, n_elems, per)) + [n_elems]
+        if len(bounds) > 2 and bounds[-1] - bounds[-2] < per // 4:
+            del bounds[-2]                       # fold a small tail into the last bucket
+        return bounds
+
+    def _event(self, i):
+        while len(self._events) <= i:
+            self._events.append(_dev.Event())
+        return self._events[i]
+
+    def _pipeline(self, pd, dtype, stream, consume):
+        """pack -> in-place allreduce -> consume(begin, end), bucketed.
+
+        Stream `stream` runs pack and consume; the allreduce of every bucket is
+        issued on a side stream as soon as that bucket is packed (events), so it
+        overlaps the packing of later buckets and the consumption of earlier
+        ones.  With one rank there is nothing to reduce and no side stream."""
+        buf = self.gpu_buffer_a
+        type_id = _communication_utility._get_nccl_type_id(dtype)
+        itemsize = _dev.dtype_itemsize(dtype)
+        n = pd.n_elems
+        debug = config.is_debug()
+        if debug:
+            self._check_ready_to_allreduce_meta(n, dtype)
+        bounds = self._bucket_bounds(n, itemsize)
+        nb = len(bounds) - 1
+        if self.size == 1:
+            _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+            # a one-rank SUM is the identity: nothing to launch (the reference
+            # would copy A to B here)
+            self.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM,
+                                     stream.ptr)
+            if debug:
+                self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
+            consume(0, n)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = _dev.Stream(non_blocking=True)
+        cs = self._comm_stream
+        for b in range(nb):
+            lo, hi = bounds[b], bounds[b + 1]
+            _memory_utility._batched_pack_params(pd, buf, dtype, stream, elem_begin=lo,
+                                                 elem_end=hi)
+            ev = self._event(2 * b)
+            ev.record(stream)
+            cs.wait_event(ev)
+            self.nccl_comm.allReduce(buf.ptr() + lo * itemsize, buf.ptr() + lo * itemsize,
+                                     hi - lo, type_id, nccl.NCCL_SUM, cs.ptr)
+            self._event(2 * b + 1).record(cs)
+        for b in range(nb):
+            stream.wait_event(self._event(2 * b + 1))
+            if debug:
+                self._ensure_all_finite_device(buf.ptr() + bounds[b] * itemsize, dtype,
+                                               bounds[b + 1] - bounds[b], stream)
+            consume(bounds[b], bounds[b + 1])
+
+    # -------------------------------------------------- debug-mode checks --
+    def _check_ready_to_allreduce_meta(self, n_elems, dtype):
+        """Shape agreement across ranks (``mpi_communicator_base.py:717-728``)."""
+        my_shapes = (((n_elems,), str(dtype)), (n_elems,), str(dtype))
+        all_shapes = self.gather_obj((self.rank, my_shapes))
+        if self.rank == 0:
+            for rank, shapes in all_shapes:
+                if my_shapes != shapes:
+                    raise ValueError('Shape does not match: {}'
+                                     ' at rank 0 while {} at rank {}'
+                                     .format(my_shapes, shapes, rank))
+
+    def _ensure_all_finite_device(self, ptr, dtype, n_elems, stream):
+        """``_ensure_all_finite`` (``mpi_communicator_base.py:730-733``)."""
+        lib = _lib.get()
+        if self._finite_flag is None:
+            self._finite_flag = _dev.DeviceArray.zeros((1,), np.int32)
+        flag = self._finite_flag
+        lib.gp_memset_async(flag.data.ptr, 0, 4, stream.ptr)
+        lib.gp_check_finite(ptr, _dev.dtype_id(dtype), n_elems, flag.data.ptr, stream.ptr)
+        if int(flag.get(stream)[0]) != 0:
+            raise ValueError('Parameters diverged after allreduce.')
+
+    # ----------------------------------------------- _multi_node_mean_nccl --
+    def _multi_node_mean_nccl(self, sendbuf, recvbuf, n_elems, dtype, stream=None):
+        """``pure_nccl_communicator.py:154-193``: ``recvbuf = mean over ranks of
+        sendbuf`` for ``DeviceMemory``-like buffers (used by MNBN)."""
+        if stream is None:
+            stream = _dev.Stream.null
+        if config.is_debug():
+            stream.synchronize()
+            self._check_ready_to_allreduce_meta(n_elems, dtype)
+        self._init_comms()
+        type_id = _communication_utility._get_nccl_type_id(dtype)
+        self.nccl_comm.allReduce(sendbuf.ptr(), recvbuf.ptr(), n_elems,
+                                 type_id, nccl.NCCL_SUM, stream.ptr)
+        _lib.get().gp_scale(recvbuf.ptr(), _dev.dtype_id(dtype), n_elems, 1.0 / self.size,
+                            stream.ptr)
+        if config.is_debug():
+            self._ensure_all_finite_device(recvbuf.ptr(), dtype, n_elems, stream)
+
+    # ----------------------------------------------------- fused update ----
+    def multi_node_mean_grad_and_update(self, model, optimizer, zero_fill=False, stream=None):
+        """``multi_node_mean_grad(model, zero_fill)`` followed by
+        ``optimizer.update(None)`` as ONE pipeline: pack, in-place allreduce, and
+        a fused unpack + descale + MomentumSGD / Adam kernel that reads every
+        mean gradient once.
+
+        Returns False -- having done nothing -- when the optimizer cannot be
+        fused (hooks, loss scaling, custom or disabled update rules, fp32 master
+        weights, mixed gradient/parameter dtypes); the caller then runs the two
+        reference steps.  Observable state afterwards equals the reference's:
+        ``optimizer.t`` and every ``rule.t`` advanced by one, states created,
+        and (``self.write_grad``) ``param.grad`` holding the mean.
+        """
+        plan = _fusion_plan(model, optimizer, zero_fill)
+        if plan is None:
+            return False
+        if stream is None:
+            stream = _dev.Stream.null
+        self._init_comms()
+        params, others = plan
+        dtype = self._allreduce_dtype()
+
+        # zero_fill + state init + t bookkeeping, exactly as
+        # GradientMethod.update / UpdateRule.update would do
+        # (chainer/optimizer.py:857-894, 236-250, 473-484)
+        for p in params:
+            if p.grad is None:
+                p.grad = _dev.zeros_like(p.data)     # ParamsData zero_fill (:40-42)
+        optimizer.t += 1
+        for p in others:                              # uninitialised parameters only
+            rule = p.update_rule
+            if rule is not None and rule.enabled:
+                rule.t += 1
+        groups = {}
+        order = []
+        for i, p in enumerate(params):
+            rule = p.update_rule
+            rule.t += 1
+            rule._init_states(p)
+            key = rule.fused_key()
+            if key not in groups:
+                groups[key] = []
+                order.append(key)
+            groups[key].append(i)
+
+        if self._table_fused is None:
+            self._table_fused = _memory_utility.DeviceTable()
+        extra = []
+        for p in params:
+            st = p.update_rule.state
+            extra.append((p.data, [st[k] for k in p.update_rule.state_names]))
+        pd = _memory_utility.ParamsData(params, 'grad', False, extra_ptrs=extra, stream=stream,
+                                        table=self._table_fused)
+        n_elems = pd.n_elems
+        needs_sync = self._prepare_allreduce_pack_buffer(dtype, n_elems)
+        if stream != _dev.Stream.null and needs_sync:
+            _dev.Stream.null.synchronize()
+        if n_elems == 0:
+            return True
+
+        lib = _lib.get()
+        buf_id = _dev.dtype_id(dtype)
+        scale = 1.0 / self.size
+        wg = 1 if self.write_grad else 0
+
+        if len(order) == 1:
+            key = order[0]
+            tables = [(key, pd)]
+        else:
+            # per-parameter hyperparameters / step counts: one launch per group,
+            # each over its own segment list (buf_off points into the shared buffer)
+            tables = []
+            for key in order:
+                idx = groups[key]
+                sub = _memory_utility.ParamsData(
+                    [params[i] for i in idx], 'grad', False,
+                    extra_ptrs=[extra[i] for i in idx], stream=stream,
+                    buf_offsets=pd.host_csum[idx])
+                tables.append((key, sub))
+
+        def launch(key, t, begin, end):
+            if key[0] == 'momentum_sgd':
+                lib.gp_unpack_momentum_sgd(self.gpu_buffer_a.ptr(), buf_id, t.d_csum, t.d_segs,
+                                           t.n_params, begin, end, scale, key[1], key[2], wg,
+                                           stream.ptr)
+            else:
+                lib.gp_unpack_adam(self.gpu_buffer_a.ptr(), buf_id, t.d_csum, t.d_segs,
+                                   t.n_params, begin, end, scale, key[1], key[2], key[3], key[4],
+                                   key[5], key[6], key[7], key[8], key[9], wg, stream.ptr)
+
+        if len(tables) == 1:
+            def consume(begin, end):
+                launch(tables[0][0], tables[0][1], begin, end)
+        else:
+            state = {'done': False}
+
+            def consume(begin, end):
+                # grouped launches cover their whole lists; run them once the
+                # last bucket has been reduced
+                if end == n_elems and not state['done']:
+                    state['done'] = True
+                    for key, t in tables:
+                        launch(key, t, 0, t.n_elems)
+            # the grouped path needs the whole buffer: no bucket overlap
+        self._pipeline(pd, dtype, stream, consume)
+        self._keep_alive = (pd, tables)
+        return True
+
+
+def _fusion_plan(model, optimizer, zero_fill):
+    """Decide whether ``optimizer.update(None)`` can be fused; returns
+    (params_in_layout_order, other_params) or None."""
+    if getattr(optimizer, '_loss_scale', None) is not None:
+        return None
+    if getattr(optimizer, '_loss_scaling_is_dynamic', False):
+        return None
+    hookable = getattr(optimizer, '_hookable', None)
+    if hookable is None or hookable.has_hooks():
+        return None
+    if getattr(optimizer, 'target', None) is not model:
+        return None
+    params = _memory_utility.extract_params_set_grad(model, zero_fill)
+    chosen = set(id(p) for p in params)
+    others = [p for p in model.params() if id(p) not in chosen]
+    for p in params:
+        rule = getattr(p, 'update_rule', None)
+        if rule is None or getattr(rule, 'fused_kind', None) is None:
+            return None
+        if not rule.enabled or rule._use_fp32_update or rule._hookable.has_hooks():
+            return None
+        if getattr(p, '_loss_scale', None) is not None:
+            return None
+        ddt = _dev.array_dtype(p.data)
+        if isinstance(ddt, str) or ddt not in (np.float16, np.float32, np.float64):
+            return None
+        if p.grad is not None and _dev.array_dtype(p.grad) != ddt:
+            return None
+        if rule.fused_kind == 'adam':
+            interm = np.float32 if ddt == np.float16 else ddt.type
+            rule._check_eps(interm)
+    for p in others:
+        # An initialised parameter outside the mean-grad set (grad None with
+        # zero_fill=False) is still updated by the reference's optimizer.update():
+        # reallocate_cleared_grads() gives it a zero gradient first
+        # (chainer/optimizer.py:834-851, 881).  Leave that case to the unfused path.
+        if p.data is not None:
+            return None
+        rule = getattr(p, 'update_rule', None)
+        if rule is not None and rule._hookable.has_hooks():
+            return None
+    return params, others

@@ -1,0 +1,319 @@
+"""``Hyperparameter`` / ``UpdateRule`` / ``Optimizer`` / ``GradientMethod``.
+
+Mirror of the parts of ``chainer/optimizer.py`` that the gradient path drives:
+
+* ``Hyperparameter`` with parent chain              -- ``optimizer.py:92-145``
+* ``UpdateRule.update / __update / _init_states / update_core``
+                                                    -- ``optimizer.py:236-336, 473-484``
+* ``Optimizer.setup / add_hook / call_hooks / loss scaling bookkeeping``
+                                                    -- ``optimizer.py:560-791``
+* ``GradientMethod.update / reallocate_cleared_grads`` -- ``optimizer.py:834-894``
+
+``update_core`` always dispatches to ``update_core_gpu``: this package has no
+CPU path (the reference's ``update_core_cpu`` lives in ``oracle/`` as the
+checker only).
+"""
+import collections
+import copy
+import math
+import warnings
+
+import numpy as np
+
+from chainer_b200 import device as _dev
+
+
+class Hyperparameter(object):
+    """Set of hyperparameter entries with a parent to fall back to
+    (``optimizer.py:92-145``)."""
+
+    def __init__(self, parent=None):
+        self._parent = parent
+
+    def __getattr__(self, name):
+        if '_parent' not in self.__dict__:
+            raise AttributeError('_parent is not set up yet')
+        parent = self.__dict__['_parent']
+        if parent is None:
+            raise AttributeError(name)
+        return getattr(parent, name)
+
+    def __repr__(self):
+        d = self.get_dict()
+        keys = sorted(d.keys())
+        values_repr = ', '.join('%s=%s' % (k, d[k]) for k in keys)
+        return 'Hyperparameter(%s)' % values_repr
+
+    @property
+    def parent(self):
+        return self._parent
+
+    def get_dict(self):
+        d = {} if self._parent is None else self._parent.get_dict()
+        for k, v in self.__dict__.items():
+            if k != '_parent':
+                d[k] = v
+        return d
+
+
+class HyperparameterProxy(object):
+    """``optimizer.HyperparameterProxy``: alias of ``self.hyperparam.<name>``."""
+
+    def __init__(self, attr_name):
+        self._attr_name = attr_name
+        self.__doc__ = 'Alias to ``self.hyperparam.{}``'.format(attr_name)
+
+    def __get__(self, obj, type=None):
+        if obj is None:
+            return self
+        return getattr(obj.hyperparam, self._attr_name)
+
+    def __set__(self, obj, value):
+        setattr(obj.hyperparam, self._attr_name, value)
+
+
+class _Hookable(object):
+    def __init__(self):
+        self._pre = collections.OrderedDict()
+        self._post = collections.OrderedDict()
+
+    def add_hook(self, hook, name=None, timing='auto'):
+        if not callable(hook):
+            raise TypeError('hook function must be callable')
+        if timing not in ('pre', 'post', 'auto'):
+            raise ValueError("timing must be one of ('pre', 'post', 'auto')")
+        if timing == 'auto':
+            timing = getattr(hook, 'timing', 'pre')
+        if name is None:
+            name = getattr(hook, 'name', getattr(hook, '__name__', None))
+            if name is None:
+                raise ValueError('the name of the hook function is not specified')
+        if name in self._pre or name in self._post:
+            raise KeyError('hook "{}" already exists'.format(name))
+        (self._pre if timing == 'pre' else self._post)[name] = hook
+
+    def remove_hook(self, name):
+        if name in self._pre:
+            del self._pre[name]
+        elif name in self._post:
+            del self._post[name]
+        else:
+            raise KeyError('hook "{}" does not exist'.format(name))
+
+    def has_hooks(self):
+        return bool(self._pre) or bool(self._post)
+
+    def call_hooks(self, timing, args):
+        for hook in list((self._pre if timing == 'pre' else self._post).values()):
+            hook(*args)
+
+
+class UpdateRule(object):
+    """Base class of all update rules (``optimizer.py:148-530``)."""
+
+    is_elementwise = False
+
+    def __init__(self, parent_hyperparam=None):
+        self._state = None
+        self.enabled = True
+        self.hyperparam = Hyperparameter(parent_hyperparam)
+        self.t = 0
+        self._use_fp32_update = False
+        self._fp32_param = None
+        self._hookable = _Hookable()
+
+    @property
+    def state(self):
+        return self._state
+
+    def add_hook(self, hook, name=None, timing='auto'):
+        self._hookable.add_hook(hook, name, timing)
+
+    def remove_hook(self, name):
+        self._hookable.remove_hook(name)
+
+    def update(self, param):
+        """``UpdateRule.update`` (``optimizer.py:236-250``)."""
+        if not self.enabled:
+            return
+        self.t += 1
+        self.__update(param)
+
+    def __update(self, param):
+        # ``optimizer.py:252-305`` without the ChainerX branches
+        is_initialized = param.data is not None
+        loss_scale = getattr(param, '_loss_scale', None)
+        if self._use_fp32_update and is_initialized and param.dtype == np.float16:
+            raise NotImplementedError(
+                'use_fp32_update for float16 parameters is not implemented on this path yet')
+        if is_initialized:
+            self._init_states(param)
+            if loss_scale is not None and param.grad is not None:
+                from chainer_b200 import _lib
+                g = param.grad
+                _lib.get().gp_scale(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
+                                    _dev.array_size(g), 1.0 / loss_scale, 0)
+        self._hookable.call_hooks('pre', (self, param))
+        self.update_core(param)
+        self._hookable.call_hooks('post', (self, param))
+
+    def update_core(self, param):
+        self.update_core_gpu(param)
+
+    def update_core_gpu(self, param):
+        raise NotImplementedError
+
+    def init_state(self, param):
+        pass
+
+    def _init_states(self, param):
+        """``optimizer.py:473-484``: lazy ``init_state`` on first use."""
+        if self._state is None:
+            self._state = {}
+            self.init_state(param)
+
+    def use_fp32_update(self, flag=True):
+        self._use_fp32_update = flag
+
+    def serialize(self, serializer):
+        """``optimizer.py:433-471``: ``t`` and the state arrays by name."""
+        self.t = serializer('t', self.t)
+        if self._state is not None:
+            for key in self._state:
+                self._state[key] = serializer(key, self._state[key])
+
+
+class Optimizer(object):
+    """Base class of all numerical optimizers (``optimizer.py:533-791``)."""
+
+    target = None
+    t = 0
+    epoch = 0
+    _loss_scale = None
+    _loss_scale_max = 65504
+    _loss_scaling_is_dynamic = False
+    use_auto_new_epoch = False
+
+    def __init__(self):
+        self._hookable = _Hookable()
+
+    def setup(self, link):
+        if not hasattr(link, 'namedparams'):
+            raise TypeError('optimization target must be a link')
+        self.target = link
+        self.t = 0
+        self.epoch = 0
+        self._hookable = _Hookable()
+        return self
+
+    def update(self, lossfun=None, *args, **kwds):
+        raise NotImplementedError
+
+    def new_epoch(self, auto=False):
+        self.epoch += 1
+
+    def add_hook(self, hook, name=None, timing='auto'):
+        if self.target is None:
+            raise RuntimeError('call `setup` method before `add_hook` method')
+        self._hookable.add_hook(hook, name, timing)
+
+    def remove_hook(self, name):
+        self._hookable.remove_hook(name)
+
+    def call_hooks(self, timing='pre'):
+        for hook in list((self._hookable._pre if timing == 'pre'
+                          else self._hookable._post).values()):
+            self.call_hook(hook)
+
+    def call_hook(self, hook):
+        hook(self)
+
+    def loss_scaling(self, interval=1000, scale=None):
+        """``optimizer.py:736-761``."""
+        if scale is None:
+            self._loss_scaling_is_dynamic = True
+            if interval < 1:
+                raise ValueError('interval must be greater than or equal to 1.'
+                                 ' Actual: {}'.format(interval))
+            self._loss_scale = 1.0
+            self._loss_scaling_multiplier = math.pow(2.0, 1.0 / interval)
+            self._loss_scaling_isnan_ever = False
+        else:
+            if scale <= 0:
+                raise ValueError('loss_scale must be a positive number. '
+                                 'Actual: {}'.format(scale))
+            self._loss_scale = scale
+
+    def set_loss_scale(self, loss_scale):
+        self.loss_scaling(scale=loss_scale)
+
+    def serialize(self, serializer):
+        self.t = serializer('t', self.t)
+        self.epoch = serializer('epoch', self.epoch)
+        for name, param in self.target.namedparams():
+            rule = getattr(param, 'update_rule', None)
+            if rule is not None:
+                rule.serialize(serializer[name])
+
+
+class GradientMethod(Optimizer):
+    """``optimizer.py:794-894``."""
+
+    def __init__(self):
+        super(GradientMethod, self).__init__()
+        self.hyperparam = Hyperparameter()
+        self._use_fp32_update = False
+
+    def setup(self, link):
+        super(GradientMethod, self).setup(link)
+        for param in link.params():
+            param.update_rule = self.create_update_rule()
+            if self._use_fp32_update:
+                param.update_rule.use_fp32_update()
+        return self
+
+    def reallocate_cleared_grads(self):
+        """``optimizer.py:834-851``: zeros for every gradient that is None."""
+        for name, param in self.target.namedparams(False):
+            if param.grad is None:
+                param.grad = _dev.zeros_like(param.data)
+
+    def call_hook(self, hook):
+        super(GradientMethod, self).call_hook(hook)
+        self.reallocate_cleared_grads()
+
+    def update(self, lossfun=None, *args, **kwds):
+        """``optimizer.py:857-894``."""
+        if lossfun is not None:
+            use_cleargrads = getattr(self, '_use_cleargrads', True)
+            loss = lossfun(*args, **kwds)
+            if use_cleargrads:
+                self.target.cleargrads()
+            else:
+                self.target.zerograds()
+            loss.backward(loss_scale=self._loss_scale)
+            del loss
+
+        self.reallocate_cleared_grads()
+        self.call_hooks('pre')
+
+        self.t += 1
+        for param in self.target.params():
+            param.update()
+
+        self.reallocate_cleared_grads()
+        self.call_hooks('post')
+
+    def use_cleargrads(self, use=True):
+        warnings.warn('GradientMethod.use_cleargrads is deprecated.', DeprecationWarning)
+        self._use_cleargrads = use
+
+    def use_fp32_update(self, flag=True):
+        self._use_fp32_update = flag
+        link = getattr(self, 'target', None)
+        if link is not None:
+            for param in link.params():
+                param.update_rule.use_fp32_update()
+
+    def create_update_rule(self):
+        raise NotImplementedError

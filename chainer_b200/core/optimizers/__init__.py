@@ -1,0 +1,2 @@
+from chainer_b200.core.optimizers.adam import Adam, AdamRule  # NOQA
+from chainer_b200.core.optimizers.momentum_sgd import MomentumSGD, MomentumSGDRule  # NOQA

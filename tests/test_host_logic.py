@@ -1,0 +1,484 @@
+"""Host-logic tests on CPU: the product's Python layer driven against the
+oracle-backed double of libgradpath (tests/fake_lib.py).  They mirror the
+reference's own tests of this path:
+
+* tests/chainermn_tests/communicator_tests/test_communicator.py:191-202, 242-319,
+  346-425, 453-461, 494-512, 1004-1022
+* tests/chainermn_tests/optimizer_tests/test_multi_node_optimizer.py:20-235
+* tests/chainermn_tests/optimizer_tests/test_double_buffering_optimizer.py:23-98
+"""
+import numpy as np
+import pytest
+
+import chainer_b200
+from chainer_b200 import config
+from chainer_b200.communicators import _control_plane
+from chainer_b200.communicators.pure_nccl_communicator import PureNcclCommunicator
+from chainer_b200.core import link as L
+from oracle import gradpath as og
+from tests import fake_lib
+from tests.helpers import assert_bits_equal
+
+
+@pytest.fixture
+def fake():
+    f, prev = fake_lib.install()
+    _control_plane.reset_world()
+    yield f
+    fake_lib.uninstall(prev)
+    config.set_debug(False)
+    config.set_dtype(None)
+
+
+class Linear(L.Link):
+    """Stand-in of chainer.links.Linear(in, out): W (out, in) and b (out,);
+    in_size None leaves W uninitialised like the reference's lazy Linear."""
+
+    def __init__(self, in_size, out_size, dtype=np.float32):
+        super(Linear, self).__init__()
+        with self.init_scope():
+            self.W = L.Parameter(None if in_size is None else
+                                 np.zeros((out_size, in_size), dtype=dtype))
+            self.b = L.Parameter(np.zeros((out_size,), dtype=dtype))
+
+
+class ExampleModel(L.Chain):
+    """tests/chainermn_tests/communicator_tests/test_communicator.py:30-41"""
+
+    def __init__(self, dtype=np.float32):
+        super(ExampleModel, self).__init__()
+        with self.init_scope():
+            self.a = Linear(2, 3, dtype)
+            self.b = Linear(3, 4, dtype)
+            self.c = Linear(None, 5, dtype)
+
+
+class ExampleMixedModel(L.Chain):
+    """test_communicator.py:44-57: float16 / float32 layers alternate."""
+
+    def __init__(self):
+        super(ExampleMixedModel, self).__init__()
+        with self.init_scope():
+            self.a = Linear(2, 3, np.float16)
+            self.b = Linear(3, 4, np.float32)
+            self.c = Linear(4, 5, np.float16)
+            self.d = Linear(5, 6, np.float32)
+
+
+def _fill_grads(model, rank):
+    model.a.W.grad = np.full_like(model.a.W.data, rank)
+    model.a.b.grad = np.full_like(model.a.b.data, rank)
+    model.b.W.grad = np.full_like(model.b.W.data, rank + 1)
+    model.b.b.grad = np.full_like(model.b.b.data, rank + 1)
+    model.c.b.grad = np.full_like(model.c.b.data, rank + 2)
+
+
+# --------------------------------------------------------------- config API --
+def test_create_communicator_and_config(fake):
+    comm = chainer_b200.create_communicator('pure_nccl')
+    assert isinstance(comm, PureNcclCommunicator)
+    assert (comm.rank, comm.size, comm.intra_rank, comm.intra_size, comm.inter_rank,
+            comm.inter_size) == (0, 1, 0, 1, 0, 1)
+    assert comm.get_config('batched_copy') is True
+    assert comm.get_config('allreduce_grad_dtype') is None
+    comm.set_config('batched_copy', False)
+    assert comm.get_config('batched_copy') is False
+    comm.set_config('allreduce_grad_dtype', np.float16)
+    assert comm.get_config('allreduce_grad_dtype') == np.float16
+    comm.set_config('allreduce_grad_dtype', None)
+    assert comm.get_config('allreduce_grad_dtype') is None
+    with pytest.raises(ValueError):
+        comm.set_config('allreduce_grad_dtype', np.int32)       # test_communicator.py:494-512
+    with pytest.raises(ValueError):
+        comm.set_config('no_such_config')
+    with pytest.raises(KeyError):
+        comm.get_config('no_such_config')
+    comm._configs['foobar'] = 1                                  # test_communicator.py:1015-1022
+    assert comm.get_config('foobar') == 1
+    del comm._configs['foobar']
+    with pytest.raises(ValueError):
+        chainer_b200.create_communicator('no_such_communicator')
+    with pytest.raises(ValueError):
+        chainer_b200.create_communicator('naive', allreduce_grad_dtype=np.float16)
+    comm._init_comms()
+    comm.finalize()
+    assert comm.nccl_comm is None
+
+
+def test_library_missing_fails_loudly(monkeypatch, tmp_path):
+    from chainer_b200 import _lib
+    prev = _lib.set_backend_for_testing(None)
+    monkeypatch.setenv('CHAINER_B200_LIBGRADPATH', str(tmp_path / 'nope.so'))
+    try:
+        with pytest.raises(ImportError):
+            _lib.load()
+        with pytest.raises(ImportError):
+            chainer_b200.create_communicator('pure_nccl')
+    finally:
+        _lib.set_backend_for_testing(prev)
+
+
+def test_host_arrays_rejected_by_real_backend():
+    """Without the test double, NumPy arrays are an unsupported array module
+    (reference: _memory_utility.py:50-52)."""
+    from chainer_b200 import device
+    with pytest.raises(ValueError):
+        device.device_ptr(np.zeros(3, np.float32))
+
+
+# ------------------------------------------------------ multi_node_mean_grad --
+def test_multi_node_mean_grad_single_rank(fake):
+    """check_multi_node_mean_grad (test_communicator.py:252-269) at size 1, twice."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    for _ in range(2):
+        _fill_grads(model, comm.rank)
+        comm.multi_node_mean_grad(model)
+        base = (comm.size - 1.0) / 2
+        np.testing.assert_allclose(model.a.W.grad, (base + 0) * np.ones((3, 2)))
+        np.testing.assert_allclose(model.a.b.grad, (base + 0) * np.ones((3,)))
+        np.testing.assert_allclose(model.b.W.grad, (base + 1) * np.ones((4, 3)))
+        np.testing.assert_allclose(model.b.b.grad, (base + 1) * np.ones((4,)))
+        np.testing.assert_allclose(model.c.b.grad, (base + 2) * np.ones((5,)))
+    assert model.c.W.grad is None                      # uninitialised W is skipped
+
+
+def test_multi_node_mean_grad_empty_and_zero_fill(fake):
+    """check_multi_node_mean_grad_empty / _empty_half (test_communicator.py:272-319)."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    _fill_grads(model, 0)
+    model.c.b.grad = None
+    comm.multi_node_mean_grad(model, zero_fill=False)
+    assert model.c.b.grad is None                      # skipped, not created
+    comm.multi_node_mean_grad(model, zero_fill=True)
+    assert model.c.b.grad is not None                  # created as zeros
+    np.testing.assert_array_equal(model.c.b.grad, np.zeros(5, np.float32))
+
+
+def test_layout_is_sorted_namedparams(fake):
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    rng = np.random.default_rng(0)
+    for _, p in model.namedparams():
+        if p.data is not None:
+            p.grad = rng.standard_normal(p.data.shape).astype(np.float32)
+    names = [n for n, p in sorted(model.namedparams()) if p.data is not None]
+    assert names == ['/a/W', '/a/b', '/b/W', '/b/b', '/c/b']
+    want = og.pack([p.grad for _, p in sorted(model.namedparams()) if p.data is not None],
+                   np.float32)
+    comm.multi_node_mean_grad(model)
+    from tests.fake_lib import _view
+    got = _view(comm.gpu_buffer_a.ptr(), want.size, np.float32)
+    assert_bits_equal(np.array(got), want, 'packed layout')
+
+
+@pytest.mark.parametrize('global_dtype,allreduce_dtype,expected', [
+    # the table of create_communicator's docstring (communicators/__init__.py:43-53)
+    ('float32', None, og.NCCL_FLOAT32), ('float32', np.float16, og.NCCL_FLOAT16),
+    ('float32', np.float32, og.NCCL_FLOAT32), ('float16', None, og.NCCL_FLOAT16),
+    ('float16', np.float32, og.NCCL_FLOAT32), ('mixed16', None, og.NCCL_FLOAT16),
+    ('mixed16', np.float32, og.NCCL_FLOAT32), (None, np.float64, og.NCCL_FLOAT64),
+    (None, 'bfloat16', og.NCCL_BFLOAT16),
+])
+@pytest.mark.parametrize('batched_copy', [True, False])
+def test_mixed_dtype_model_and_nccl_dtype(fake, global_dtype, allreduce_dtype, expected,
+                                          batched_copy):
+    """test_communicator.py:346-425: the dtype id handed to nccl_comm.allReduce."""
+    config.set_dtype(global_dtype)
+    comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=allreduce_dtype,
+                                            batched_copy=batched_copy)
+    comm._init_comms()
+    seen = []
+    real = comm.nccl_comm.allReduce
+
+    def spy(sendbuf, recvbuf, count, datatype, op, stream):
+        seen.append(datatype)
+        return real(sendbuf, recvbuf, count, datatype, op, stream)
+    comm.nccl_comm.allReduce = spy
+    model = ExampleMixedModel()
+    for k, lk in enumerate([model.a, model.b, model.c, model.d]):
+        lk.W.grad = np.full_like(lk.W.data, k + 1)
+        lk.b.grad = np.full_like(lk.b.data, k + 1)
+    comm.multi_node_mean_grad(model)
+    assert seen == [expected]
+    for k, lk in enumerate([model.a, model.b, model.c, model.d]):
+        assert lk.W.grad.dtype == lk.W.data.dtype
+        np.testing.assert_allclose(lk.W.grad.astype(np.float64), k + 1)
+        np.testing.assert_allclose(lk.b.grad.astype(np.float64), k + 1)
+
+
+def test_non_float_gradient_rejected(fake):
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    _fill_grads(model, 0)
+    model.a.b.grad = np.zeros(3, np.int32)
+    with pytest.raises(ValueError):
+        comm.multi_node_mean_grad(model)
+
+
+def test_debug_mode_detects_divergence(fake):
+    """test_communicator.py:453-461: NaN gradients + debug -> 'diverged'."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    _fill_grads(model, 0)
+    model.b.W.grad[1, 2] = np.nan
+    config.set_debug(True)
+    with pytest.raises(ValueError, match='.* diverged .*'):
+        comm.multi_node_mean_grad(model)
+    config.set_debug(False)
+    comm.multi_node_mean_grad(model)                   # no check without debug
+
+
+def test_bcast_data_single_rank(fake):
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = ExampleModel()
+    model.a.W.data[...] = 3
+    comm.bcast_data(model)
+    np.testing.assert_array_equal(model.a.W.data, np.full((3, 2), 3, np.float32))
+    names = [c[0] for c in fake.calls]
+    assert 'gp_pack' in names and 'gp_unpack_scale' in names
+
+
+def test_multi_node_mean_nccl_on_device_memory(fake):
+    """_multi_node_mean_nccl(sendbuf, recvbuf, n_elems, dtype) as MNBN calls it
+    (chainermn/functions/batch_normalization.py:57-60), stream=None."""
+    from chainer_b200.communicators._memory_utility import DeviceMemory
+    comm = chainer_b200.create_communicator('pure_nccl')
+    a, b = DeviceMemory(), DeviceMemory()
+    a.assign(32)
+    b.assign(32)
+    from tests.fake_lib import _view
+    _view(a.ptr(), 8, np.float32)[...] = np.arange(8)
+    comm._multi_node_mean_nccl(a, b, 8, np.dtype(np.float32))
+    np.testing.assert_array_equal(_view(b.ptr(), 8, np.float32), np.arange(8, dtype=np.float32))
+
+
+# ------------------------------------------------------- multi-node optimizer --
+def _model_with_values(seed=0, dtype=np.float32):
+    model = ExampleModel(dtype)
+    rng = np.random.default_rng(seed)
+    for _, p in sorted(model.namedparams()):
+        if p.data is not None:
+            p.data[...] = rng.standard_normal(p.data.shape).astype(dtype)
+    return model
+
+
+def _set_grads(model, seed):
+    rng = np.random.default_rng(seed)
+    for _, p in sorted(model.namedparams()):
+        if p.data is not None:
+            p.grad = (rng.standard_normal(p.data.shape) * 1e-2).astype(p.data.dtype)
+
+
+@pytest.mark.parametrize('opt_name', ['momentum_sgd', 'adam'])
+@pytest.mark.parametrize('fused', [True, False])
+def test_multi_node_optimizer_protocol(fake, opt_name, fused):
+    """test_multi_node_optimizer.py:51-110: first update() only broadcasts
+    (t == 0), the second updates (t == 1, every rule.t == 1) and param.grad holds
+    the mean; results equal the oracle whether or not the fused path is taken."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values()
+    ref = _model_with_values()
+    make = (lambda: chainer_b200.MomentumSGD(lr=0.1, momentum=0.9)) if opt_name == 'momentum_sgd' \
+        else (lambda: chainer_b200.Adam(alpha=0.01))
+    actual = make()
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    if not fused:
+        actual.add_hook(lambda o: None, name='noop')          # any hook disables fusion
+    _set_grads(model, 1)
+    opt.update()
+    assert actual.t == 0
+    assert all(p.update_rule.t == 0 for p in model.params())
+    np.testing.assert_array_equal(model.a.W.data, ref.a.W.data)   # bcast only
+
+    states = {}
+    for step in range(1, 4):
+        _set_grads(model, 10 + step)
+        _set_grads(ref, 10 + step)
+        fake.calls[:] = []
+        opt.update()
+        names = [c[0] for c in fake.calls]
+        if fused:
+            assert ('gp_unpack_momentum_sgd' if opt_name == 'momentum_sgd' else 'gp_unpack_adam') in names
+            assert 'gp_unpack_scale' not in names
+            assert names.count('gp_pack') == 1
+        else:
+            assert 'gp_unpack_scale' in names
+        assert actual.t == step
+        for name, p in sorted(model.namedparams()):
+            assert p.update_rule.t == step
+        for (name, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+            if p.data is None:
+                continue
+            st = states.setdefault(name, {k: np.zeros_like(q.data) for k in ('v', 'm')})
+            g = q.grad
+            if opt_name == 'momentum_sgd':
+                og.momentum_sgd_update(q.data, g, st['v'], 0.1, 0.9)
+            else:
+                og.adam_update_gpu(q.data, g, st['m'], st['v'], step, alpha=0.01)
+            assert_bits_equal(p.data, q.data, name)
+            assert_bits_equal(p.grad, g, name + ' grad')       # grad observable: the mean
+
+
+def test_fused_and_unfused_paths_agree_bitwise(fake):
+    results = []
+    for fused in (True, False):
+        comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=np.float16)
+        model = _model_with_values(3)
+        actual = chainer_b200.MomentumSGD(lr=0.05, momentum=0.8)
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+        opt.setup(model)
+        if not fused:
+            actual.add_hook(lambda o: None, name='noop')
+        opt.update()
+        for step in range(3):
+            _set_grads(model, 40 + step)
+            opt.update()
+        results.append([p.data.copy() for _, p in sorted(model.namedparams()) if p.data is not None])
+    for a, b in zip(*results):
+        assert_bits_equal(a, b, 'fused vs unfused')
+
+
+def test_per_parameter_hyperparameters_are_honoured(fake):
+    """UpdateRule hyperparameters override the optimizer's (optimizer.py:92-145)."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values(5)
+    ref = _model_with_values(5)
+    actual = chainer_b200.MomentumSGD(lr=0.1, momentum=0.9)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    model.a.W.update_rule.hyperparam.lr = 0.5
+    model.b.b.update_rule.enabled = True
+    opt.update()
+    _set_grads(model, 77)
+    _set_grads(ref, 77)
+    opt.update()
+    for (name, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+        if p.data is None:
+            continue
+        v = np.zeros_like(q.data)
+        og.momentum_sgd_update(q.data, q.grad, v, 0.5 if name == '/a/W' else 0.1, 0.9)
+        assert_bits_equal(p.data, q.data, name)
+
+
+def test_disabled_rule_falls_back_and_skips_update(fake):
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values(6)
+    actual = chainer_b200.MomentumSGD(lr=0.1)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    model.a.W.update_rule.enabled = False
+    before = model.a.W.data.copy()
+    opt.update()
+    _set_grads(model, 5)
+    opt.update()
+    np.testing.assert_array_equal(model.a.W.data, before)
+    assert model.a.W.update_rule.t == 0
+    assert model.a.b.update_rule.t == 1
+
+
+def test_dynamic_model_rebroadcasts(fake):
+    """test_multi_node_optimizer.py:122-235: a new link -> setup again -> the
+    next update() broadcasts (t back to 0)."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values(8)
+    actual = chainer_b200.MomentumSGD(lr=0.1)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    _set_grads(model, 1)
+    opt.update()
+    assert actual.t == 0
+    _set_grads(model, 2)
+    opt.update()
+    assert actual.t == 1
+    with model.init_scope():
+        model.d = Linear(4, 4)
+    opt.setup(model)
+    _set_grads(model, 3)
+    opt.update()
+    assert actual.t == 0                               # broadcast only
+    _set_grads(model, 4)
+    opt.update()
+    assert actual.t == 1
+    assert model.d.W.update_rule.t == 1
+
+
+def test_double_buffering_optimizer(fake):
+    """test_double_buffering_optimizer.py:43-90: means land in
+    communicated_target one call late; t increments one call late."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values(9)
+    actual = chainer_b200.MomentumSGD(lr=0.1)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm, double_buffering=True)
+    opt.setup(model)
+    _fill_grads(model, 0)
+    opt.update()                                       # bcast + deep copy
+    assert actual.t == 0 and opt.communicated_target is not None
+    _fill_grads(model, 0)
+    opt.update()                                       # swap, async mean, no update yet
+    assert actual.t == 0
+    opt.wait()
+    ct = opt.communicated_target
+    np.testing.assert_allclose(ct.a.W.grad, 0 * np.ones((3, 2)))
+    np.testing.assert_allclose(ct.b.W.grad, 1 * np.ones((4, 3)))
+    np.testing.assert_allclose(ct.c.b.grad, 2 * np.ones((5,)))
+    _fill_grads(model, 0)
+    opt.update()
+    assert actual.t == 1
+    with pytest.raises(ValueError):
+        class NotPure(object):
+            pass
+        chainer_b200.create_multi_node_optimizer(actual, NotPure(), double_buffering=True)
+
+
+def test_adam_eps_underflow_raises(fake):
+    """adam.py:176-187 via the fused path."""
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values(2)
+    actual = chainer_b200.Adam(eps=1e-60)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    opt.update()
+    _set_grads(model, 1)
+    with pytest.raises(ValueError, match='eps of Adam optimizer is too small'):
+        opt.update()
+
+
+def test_update_rule_standalone(fake):
+    """GradientMethod.update without a communicator: per-parameter update_core_gpu."""
+    model = _model_with_values(4)
+    ref = _model_with_values(4)
+    opt = chainer_b200.Adam(eta=0.5, weight_decay_rate=0.1)
+    opt.setup(model)
+    _set_grads(model, 3)
+    _set_grads(ref, 3)
+    model.c.b.grad = None                              # reallocate_cleared_grads -> zeros
+    ref.c.b.grad = np.zeros_like(ref.c.b.data)
+    opt.update()
+    assert opt.t == 1
+    for (name, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+        if p.data is None:
+            assert p.update_rule.t == 1
+            continue
+        m, v = np.zeros_like(q.data), np.zeros_like(q.data)
+        og.adam_update_gpu(q.data, q.grad, m, v, 1, eta=0.5, weight_decay_rate=0.1)
+        assert_bits_equal(p.data, q.data, name)
+        assert_bits_equal(p.update_rule.state['m'], m, name)
+
+
+def test_bucket_bounds():
+    comm = PureNcclCommunicator.__new__(PureNcclCommunicator)
+    comm.bucket_bytes = 32 << 20
+
+    class M(object):
+        size = 8
+    comm.mpi_comm = M()
+    b = comm._bucket_bounds(25557096, 4)
+    assert b[0] == 0 and b[-1] == 25557096
+    assert all(x % 1024 == 0 for x in b[:-1])
+    assert all(b[i] < b[i + 1] for i in range(len(b) - 1))
+    assert len(b) - 1 == 3                              # 102 MB / 32 MB -> 3 buckets (+ folded tail)
+    M.size = 1
+    assert comm._bucket_bounds(1000, 4) == [0, 1000]
