@@ -106,6 +106,11 @@ PROTOTYPES = {
     'gp_get_tuning': (c_int, [c_char_p, _P(c_int)]),
 }
 
+# entry points that launch exactly one of OUR kernels (counted in `launches`)
+KERNEL_FUNCS = frozenset([
+    'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
+    'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var'])
+
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes'}
 
@@ -135,6 +140,7 @@ class _Lib(object):
 
     def __init__(self, path):
         self.path = path
+        self.launches = 0      # kernels of this library launched so far
         self.cdll = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
         for name, (restype, argtypes) in PROTOTYPES.items():
             try:
@@ -154,8 +160,11 @@ class _Lib(object):
 
     def _checked(self, name, fn):
         last_error = self.cdll.gp_last_error
+        counted = name in KERNEL_FUNCS
 
         def call(*args):
+            if counted:
+                self.launches += 1
             rc = fn(*args)
             if rc != 0:
                 last_error.restype = c_char_p

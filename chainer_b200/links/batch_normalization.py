@@ -1,0 +1,135 @@
+"""MultiNodeBatchNormalization link: mirror of
+``chainermn/links/batch_normalization.py:15-147``.
+
+Constructor arguments, parameters (``gamma``, ``beta``), persistents
+(``avg_mean``, ``avg_var`` -- initialised to ZEROS like the reference, ``:57-60``
+--, ``N``), ``decay`` / ``eps`` / ``finetune`` semantics and backend validation
+follow the reference.  Only the STATISTICS are computed by this package's
+kernels (``functions/batch_normalization._NcclImpl``); the elementwise
+normalisation ``y = gamma * (x - mean) * inv_std + beta`` and ``gx`` stay on the
+framework's own path -- Chainer + CuPy in the reference
+(``chainer/functions/normalization/batch_normalization.py:46-47, 121-133``),
+``torch`` ops with ``torch.autograd`` here, since that is the array library of
+this image.
+"""
+import numpy as np
+
+from chainer_b200 import config
+from chainer_b200 import device as _dev
+from chainer_b200.core import link
+from chainer_b200.functions import batch_normalization as mnbn_functions
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _MNBNFunction(object):
+    """Builds the torch.autograd.Function lazily (torch import on first use)."""
+
+    _fn = None
+
+    @classmethod
+    def get(cls):
+        if cls._fn is not None:
+            return cls._fn
+        torch = _torch()
+
+        class MNBN(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, gamma, beta, impl, eps):
+                axis = (0,) + tuple(range(2, x.dim()))
+                x = x.contiguous()
+                mean, var = impl.get_mean_and_var(axis, gamma, x)
+                inv_std = torch.rsqrt(var + eps)
+                shape = (1, -1) + (1,) * (x.dim() - 2)
+                y = (gamma.view(shape) * (x - mean.view(shape).to(x.dtype)) *
+                     inv_std.view(shape).to(x.dtype) + beta.view(shape)).to(x.dtype)
+                ctx.impl = impl
+                ctx.save_for_backward(x, gamma, mean, inv_std)
+                ctx.mark_non_differentiable(mean, var)
+                return y, mean, var
+
+            @staticmethod
+            def backward(ctx, gy, _gm, _gv):
+                x, gamma, mean, inv_std = ctx.saved_tensors
+                axis = (0,) + tuple(range(2, x.dim()))
+                gy = gy.contiguous()
+                gbeta, ggamma = ctx.impl.get_ggamma_and_gbeta_from_x(axis, gamma, gy, x, mean,
+                                                                     inv_std)
+                shape = (1, -1) + (1,) * (x.dim() - 2)
+                inv_m = 1.0 / (x.numel() // gamma.numel())
+                x_hat = (x - mean.view(shape)) * inv_std.view(shape)
+                gx = (gamma * inv_std).view(shape) * (
+                    gy - (x_hat * ggamma.view(shape) + gbeta.view(shape)) * inv_m)
+                return gx.to(x.dtype), ggamma, gbeta, None, None
+
+        cls._fn = MNBN
+        return MNBN
+
+
+class MultiNodeBatchNormalization(link.Link):
+
+    def __init__(self, size, comm, decay=0.9, eps=2e-5, dtype=None,
+                 use_gamma=True, use_beta=True,
+                 initial_gamma=None, initial_beta=None,
+                 communication_backend='auto', device='cuda'):
+        super(MultiNodeBatchNormalization, self).__init__()
+        torch = _torch()
+        self._highprec_dtype = config.get_dtype(dtype, map_mixed16=np.float32)
+        tdt = {np.dtype(np.float16): torch.float16, np.dtype(np.float32): torch.float32,
+               np.dtype(np.float64): torch.float64}[np.dtype(self._highprec_dtype)]
+        self.comm = comm
+        self.avg_mean = torch.zeros(size, dtype=tdt, device=device)
+        self.avg_var = torch.zeros(size, dtype=tdt, device=device)
+        self.N = 0
+        self.decay = decay
+        self.eps = eps
+        self._device = device
+        self._tdt = tdt
+        self._communication_backend = \
+            mnbn_functions.get_communication_backend(comm, communication_backend)
+        with self.init_scope():
+            if use_gamma:
+                g = torch.full((size,), 1.0 if initial_gamma is None else float(initial_gamma),
+                               dtype=tdt, device=device)
+                self.gamma = link.Parameter(g)
+            if use_beta:
+                b = torch.full((size,), 0.0 if initial_beta is None else float(initial_beta),
+                               dtype=tdt, device=device)
+                self.beta = link.Parameter(b)
+
+    def _impl(self):
+        return mnbn_functions.MultiNodeBNImplSelector(
+            self.comm, self._communication_backend)(None, None)
+
+    def __call__(self, x, finetune=False, train=True):
+        torch = _torch()
+        size = self.avg_mean.shape[0]
+        gamma = self.gamma.data if hasattr(self, 'gamma') else \
+            torch.ones(size, dtype=self._tdt, device=self._device)
+        beta = self.beta.data if hasattr(self, 'beta') else \
+            torch.zeros(size, dtype=self._tdt, device=self._device)
+        if train:
+            if finetune:
+                self.N += 1
+                decay = 1. - 1. / self.N
+            else:
+                decay = self.decay
+            y, mean, var = _MNBNFunction.get().apply(x, gamma, beta, self._impl(), self.eps)
+            # running statistics (chainer/functions/normalization/
+            # batch_normalization.py:50-77): m is the LOCAL element count per channel
+            m = x.numel() // size
+            adjust = m / max(m - 1., 1.)
+            with torch.no_grad():
+                self.avg_mean.mul_(decay).add_(mean.to(self._tdt), alpha=1 - decay)
+                self.avg_var.mul_(decay).add_(var.to(self._tdt), alpha=(1 - decay) * adjust)
+            return y
+        shape = (1, -1) + (1,) * (x.dim() - 2)
+        inv_std = torch.rsqrt(self.avg_var + self.eps)
+        return (gamma.view(shape) * (x - self.avg_mean.view(shape)) * inv_std.view(shape) +
+                beta.view(shape)).to(x.dtype)
+
+    def start_finetuning(self):
+        self.N = 0
