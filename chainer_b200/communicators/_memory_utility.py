@@ -140,19 +140,20 @@ class DeviceTable(object):
 
     def __init__(self):
         h = ctypes.c_void_p()
-        _lib.get().gp_table_create(ctypes.byref(h))
+        self._lib = _lib.get()
+        self._lib.gp_table_create(ctypes.byref(h))
         self.handle = h.value
 
     def upload(self, blob, stream=None):
         out = ctypes.c_void_p()
-        _lib.get().gp_table_upload(self.handle, blob.ctypes.data, blob.nbytes,
+        self._lib.gp_table_upload(self.handle, blob.ctypes.data, blob.nbytes,
                                    _dev.stream_ptr(stream), ctypes.byref(out))
         return out.value
 
     def __del__(self):
         if getattr(self, 'handle', None):
             try:
-                _lib.get().gp_table_destroy(self.handle)
+                self._lib.gp_table_destroy(self.handle)
             except Exception:
                 pass
             self.handle = None
@@ -169,7 +170,8 @@ class HostPinnedMemory(object):
         if size > self.size:
             self._free()
             p = ctypes.c_void_p()
-            _lib.get().gp_malloc_host(ctypes.byref(p), size)
+            self._lib = _lib.get()
+            self._lib.gp_malloc_host(ctypes.byref(p), size)
             self.memory = p.value
             self.size = size
 
@@ -189,7 +191,7 @@ class HostPinnedMemory(object):
     def _free(self):
         if self.memory:
             try:
-                _lib.get().gp_free_host(self.memory)
+                self._lib.gp_free_host(self.memory)
             except Exception:
                 pass
             self.memory = None

@@ -104,6 +104,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self._table_data = None
         self._table_fused = None
         self._finite_flag = None
+        self._fused_plan = None
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -336,101 +337,209 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         reference steps.  Observable state afterwards equals the reference's:
         ``optimizer.t`` and every ``rule.t`` advanced by one, states created,
         and (``self.write_grad``) ``param.grad`` holding the mean.
-        """
-        plan = _fusion_plan(model, optimizer, zero_fill)
-        if plan is None:
-            return False
-        if stream is None:
-            stream = _dev.Stream.null
-        self._init_comms()
-        params, others = plan
-        dtype = self._allreduce_dtype()
 
-        # zero_fill + state init + t bookkeeping, exactly as
-        # GradientMethod.update / UpdateRule.update would do
-        # (chainer/optimizer.py:857-894, 236-250, 473-484)
-        for p in params:
+        The walk over the model, the fusability checks and the device tables are
+        cached in a plan that stays valid while the model structure and the
+        update rules are unchanged (version counters of ``chainer_b200.core``);
+        gradients are re-read every step because Chainer reallocates them
+        (``cleargrads``), and optimizer-level hyperparameters are re-read every
+        step because training extensions change them.
+        """
+        plan = self._fused_plan
+        if plan is None or not plan.matches(model, optimizer, zero_fill):
+            plan = _FusedPlan.build(self, model, optimizer, zero_fill)
+            self._fused_plan = plan if (plan is not None and plan.cacheable) else None
+            if plan is None:
+                return False
+        plan.run(stream if stream is not None else _dev.Stream.null)
+        return True
+
+    def invalidate_plans(self):
+        """Drop cached plans (call after replacing parameter or state arrays
+        behind the back of the Link / UpdateRule classes)."""
+        self._fused_plan = None
+
+
+def _versions():
+    from chainer_b200.core import link as _link
+    from chainer_b200.core import optimizer as _opt
+    return (_link.structure_version(), _opt.rules_version())
+
+
+class _FusedPlan(object):
+    """Everything about one (model, optimizer) pair that does not change from
+    step to step on the fused path."""
+
+    @classmethod
+    def build(cls, comm, model, optimizer, zero_fill):
+        fp = _fusion_plan(model, optimizer, zero_fill)
+        if fp is None:
+            return None
+        self = cls()
+        self.comm = comm
+        self.model = model
+        self.optimizer = optimizer
+        self.zero_fill = zero_fill
+        self.params, self.others = fp
+        self.rules = [p.update_rule for p in self.params]
+        self.other_rules = [p.update_rule for p in self.others
+                            if p.update_rule is not None and p.update_rule.enabled]
+        self.cacheable = bool(getattr(model, '_b200_versioned', False) and
+                              getattr(optimizer, '_b200_versioned', False) and
+                              all(getattr(r, '_b200_versioned', False) for r in self.rules))
+        # states are created on first use (chainer/optimizer.py:473-484)
+        for p in self.params:
+            p.update_rule._init_states(p)
+        self.versions = _versions()          # after state creation
+        for p in self.params:                # ParamsData zero_fill (_memory_utility.py:40-42)
             if p.grad is None:
-                p.grad = _dev.zeros_like(p.data)     # ParamsData zero_fill (:40-42)
-        optimizer.t += 1
-        for p in others:                              # uninitialised parameters only
-            rule = p.update_rule
-            if rule is not None and rule.enabled:
-                rule.t += 1
+                p.grad = _dev.zeros_like(p.data)
+        self.extra = []
+        for p in self.params:
+            st = p.update_rule.state
+            self.extra.append((p.data, [st[k] for k in p.update_rule.state_names]))
+        self.table = _memory_utility.DeviceTable()
+        self.pd = _memory_utility.ParamsData(self.params, 'grad', False, extra_ptrs=self.extra,
+                                             table=self.table)
+        self.grad_ptrs = self.pd.host_segs['ptr'][:, 0].copy()
+        self.seen = dict((id(g), g) for g in self.pd.arrays[:len(self.params)])
+        self.sizes = [_dev.array_size(p.data) for p in self.params]
+        self.dtypes = [_dev.array_dtype(p.data) for p in self.params]
+        # launch groups: rules with equal hyperparameters and step count.  The
+        # grouping only depends on per-rule overrides, which are version-tracked.
         groups = {}
         order = []
-        for i, p in enumerate(params):
-            rule = p.update_rule
-            rule.t += 1
-            rule._init_states(p)
-            key = rule.fused_key()
+        for i, rule in enumerate(self.rules):
+            key = rule.fused_signature()
             if key not in groups:
                 groups[key] = []
                 order.append(key)
             groups[key].append(i)
+        self.groups = []
+        if len(order) == 1:
+            self.groups.append((self.rules[0], None, self.pd))
+        else:
+            for key in order:
+                idx = np.asarray(groups[key])
+                sub = _memory_utility.ParamsData(
+                    [self.params[i] for i in idx], 'grad', False,
+                    extra_ptrs=[self.extra[i] for i in idx],
+                    buf_offsets=self.pd.host_csum[idx])
+                self.groups.append((self.rules[idx[0]], idx, sub))
+        return self
 
-        if self._table_fused is None:
-            self._table_fused = _memory_utility.DeviceTable()
-        extra = []
-        for p in params:
-            st = p.update_rule.state
-            extra.append((p.data, [st[k] for k in p.update_rule.state_names]))
-        pd = _memory_utility.ParamsData(params, 'grad', False, extra_ptrs=extra, stream=stream,
-                                        table=self._table_fused)
+    def matches(self, model, optimizer, zero_fill):
+        return (model is self.model and optimizer is self.optimizer and
+                zero_fill == self.zero_fill and self.versions == _versions())
+
+    def _refresh_grads(self, stream):
+        """Re-read every gradient pointer; re-upload the tables if any moved."""
+        params = self.params
+        grads = [p.grad for p in params]
+        seen = self.seen
+        ptrs = []
+        for i, g in enumerate(grads):
+            if g is None:
+                g = _dev.zeros_like(params[i].data)      # zero_fill
+                params[i].grad = g
+                grads[i] = g
+            if id(g) not in seen:
+                # first sight of this array object: validate it like ParamsData does
+                dt = _dev.array_dtype(g)
+                if isinstance(dt, str) or dt != self.dtypes[i]:
+                    if isinstance(dt, str) or dt not in (np.float16, np.float32, np.float64):
+                        raise ValueError('dtype must be float16, float32 or float64.')
+                    self.comm._fused_plan = None
+                    raise _PlanStale()
+                if _dev.array_size(g) != self.sizes[i]:
+                    raise ValueError('gradient of size {} for a parameter of size {}'.format(
+                        _dev.array_size(g), self.sizes[i]))
+                if len(seen) > 8192:
+                    seen.clear()
+                seen[id(g)] = g
+            try:
+                ptrs.append(g.data_ptr())
+            except AttributeError:
+                ptrs.append(_dev.device_ptr(g))
+        ptrs = np.asarray(ptrs, dtype=np.uint64)
+        if not np.array_equal(ptrs, self.grad_ptrs):
+            self.grad_ptrs = ptrs
+            self.pd.host_segs['ptr'][:, 0] = ptrs
+            self.pd.arrays[:len(grads)] = grads
+            self.pd._finish_flags()
+            self.pd.upload(stream)
+            for _, idx, sub in self.groups:
+                if idx is not None:
+                    sub.host_segs['ptr'][:, 0] = ptrs[idx]
+                    sub._finish_flags()
+                    sub.upload(stream)
+
+    def run(self, stream):
+        comm = self.comm
+        comm._init_comms()
+        dtype = comm._allreduce_dtype()
+        try:
+            self._refresh_grads(stream)
+        except _PlanStale:
+            # a gradient changed dtype: rebuild through the slow path
+            if not comm.multi_node_mean_grad_and_update(self.model, self.optimizer,
+                                                        self.zero_fill, stream):
+                raise ValueError('gradient dtype does not match its parameter')
+            return
+        # t bookkeeping of GradientMethod.update / UpdateRule.update
+        # (chainer/optimizer.py:857-894, 236-250)
+        self.optimizer.t += 1
+        for rule in self.other_rules:
+            rule.t += 1
+        for rule in self.rules:
+            rule.t += 1
+        pd = self.pd
         n_elems = pd.n_elems
-        needs_sync = self._prepare_allreduce_pack_buffer(dtype, n_elems)
+        needs_sync = comm._prepare_allreduce_pack_buffer(dtype, n_elems)
         if stream != _dev.Stream.null and needs_sync:
             _dev.Stream.null.synchronize()
         if n_elems == 0:
-            return True
-
+            return
         lib = _lib.get()
         buf_id = _dev.dtype_id(dtype)
-        scale = 1.0 / self.size
-        wg = 1 if self.write_grad else 0
-
-        if len(order) == 1:
-            key = order[0]
-            tables = [(key, pd)]
-        else:
-            # per-parameter hyperparameters / step counts: one launch per group,
-            # each over its own segment list (buf_off points into the shared buffer)
-            tables = []
-            for key in order:
-                idx = groups[key]
-                sub = _memory_utility.ParamsData(
-                    [params[i] for i in idx], 'grad', False,
-                    extra_ptrs=[extra[i] for i in idx], stream=stream,
-                    buf_offsets=pd.host_csum[idx])
-                tables.append((key, sub))
+        scale = 1.0 / comm.size
+        wg = 1 if comm.write_grad else 0
+        buf_ptr = comm.gpu_buffer_a.ptr()
+        sp = stream.ptr
+        launches = []
+        for rep, idx, t in self.groups:
+            key = rep.fused_key()                 # re-read hyperparameters (and alpha_t)
+            if key[0] == 'adam':
+                ddt = self.dtypes[0 if idx is None else idx[0]]
+                rep._check_eps(np.float32 if ddt == np.float16 else ddt.type)
+            launches.append((key, t))
 
         def launch(key, t, begin, end):
             if key[0] == 'momentum_sgd':
-                lib.gp_unpack_momentum_sgd(self.gpu_buffer_a.ptr(), buf_id, t.d_csum, t.d_segs,
-                                           t.n_params, begin, end, scale, key[1], key[2], wg,
-                                           stream.ptr)
+                lib.gp_unpack_momentum_sgd(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
+                                           begin, end, scale, key[1], key[2], wg, sp)
             else:
-                lib.gp_unpack_adam(self.gpu_buffer_a.ptr(), buf_id, t.d_csum, t.d_segs,
-                                   t.n_params, begin, end, scale, key[1], key[2], key[3], key[4],
-                                   key[5], key[6], key[7], key[8], key[9], wg, stream.ptr)
+                lib.gp_unpack_adam(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin, end,
+                                   scale, key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                                   key[8], key[9], wg, sp)
 
-        if len(tables) == 1:
+        if len(launches) == 1:
+            key0, t0 = launches[0]
+
             def consume(begin, end):
-                launch(tables[0][0], tables[0][1], begin, end)
+                launch(key0, t0, begin, end)
         else:
-            state = {'done': False}
-
             def consume(begin, end):
-                # grouped launches cover their whole lists; run them once the
-                # last bucket has been reduced
-                if end == n_elems and not state['done']:
-                    state['done'] = True
-                    for key, t in tables:
+                # grouped launches walk their own segment lists: run them once
+                # the last bucket has been reduced
+                if end == n_elems:
+                    for key, t in launches:
                         launch(key, t, 0, t.n_elems)
-            # the grouped path needs the whole buffer: no bucket overlap
-        self._pipeline(pd, dtype, stream, consume)
-        self._keep_alive = (pd, tables)
-        return True
+        comm._pipeline(pd, dtype, stream, consume)
+
+
+class _PlanStale(Exception):
+    pass
 
 
 def _fusion_plan(model, optimizer, zero_fill):

@@ -12,15 +12,47 @@ import copy
 
 from chainer_b200 import device as _dev
 
+# Bumped whenever the set of parameters, their initialised-ness or their update
+# rules change.  Lets the per-step host code (is_changed, the fused-update plan)
+# skip re-walking an unchanged model; gradients are NOT covered (they move every
+# step and are re-read every step).
+_structure_version = [0]
+
+
+def structure_version():
+    return _structure_version[0]
+
 
 class Parameter(object):
 
+    _b200_versioned = True
+
     def __init__(self, data=None, name=None):
-        self.data = data
+        self._data = data
         self.grad = None
         self.name = name
-        self.update_rule = None
+        self._update_rule = None
         self._loss_scale = None
+        _structure_version[0] += 1
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        if (value is None) != (self._data is None) or value is not self._data:
+            _structure_version[0] += 1
+        self._data = value
+
+    @property
+    def update_rule(self):
+        return self._update_rule
+
+    @update_rule.setter
+    def update_rule(self, rule):
+        _structure_version[0] += 1
+        self._update_rule = rule
 
     @property
     def array(self):
@@ -75,6 +107,8 @@ def _copy_array(a):
 
 class Link(object):
 
+    _b200_versioned = True
+
     def __init__(self, **params):
         self._params = []
         self._within_init_scope = False
@@ -96,6 +130,7 @@ class Link(object):
             value.name = name
             if name not in self._params:
                 self._params.append(name)
+            _structure_version[0] += 1
         super(Link, self).__setattr__(name, value)
 
     def add_param(self, name, data=None):
@@ -145,6 +180,7 @@ class Chain(Link):
             value.name = name
             if name not in self._children:
                 self._children.append(name)
+            _structure_version[0] += 1
         super(Chain, self).__setattr__(name, value)
 
     def add_link(self, name, link):
@@ -189,6 +225,7 @@ class ChainList(Link):
     def add_link(self, link):
         link.name = str(len(self._children))
         self._children.append(link)
+        _structure_version[0] += 1
 
     append = add_link
 

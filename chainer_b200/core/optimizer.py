@@ -23,12 +23,47 @@ import numpy as np
 from chainer_b200 import device as _dev
 
 
+# Bumped whenever something that decides HOW parameters are updated changes:
+# per-rule hyperparameter overrides, enabled flags, hooks, fp32-update,
+# loss scaling, state (de)serialisation.  Values of the optimizer-level
+# hyperparameters (lr, alpha, ...) are NOT covered: they are re-read every step.
+_rules_version = [0]
+
+
+def rules_version():
+    return _rules_version[0]
+
+
+class _Tracked(object):
+    """Attribute whose assignment bumps the rules version."""
+
+    def __init__(self, name, default):
+        self._name = '_tracked_' + name
+        self._default = default
+
+    def __get__(self, obj, type=None):
+        if obj is None:
+            return self
+        return obj.__dict__.get(self._name, self._default)
+
+    def __set__(self, obj, value):
+        _rules_version[0] += 1
+        obj.__dict__[self._name] = value
+
+
 class Hyperparameter(object):
     """Set of hyperparameter entries with a parent to fall back to
     (``optimizer.py:92-145``)."""
 
     def __init__(self, parent=None):
         self._parent = parent
+
+    def __setattr__(self, name, value):
+        # an override on a rule-level (child) hyperparameter changes the launch
+        # grouping of the fused update
+        if self.__dict__.get('_parent') is not None or name == '_parent':
+            _rules_version[0] += 1
+        object.__setattr__(self, name, value)
 
     def __getattr__(self, name):
         if '_parent' not in self.__dict__:
@@ -91,6 +126,7 @@ class _Hookable(object):
         if name in self._pre or name in self._post:
             raise KeyError('hook "{}" already exists'.format(name))
         (self._pre if timing == 'pre' else self._post)[name] = hook
+        _rules_version[0] += 1
 
     def remove_hook(self, name):
         if name in self._pre:
@@ -99,6 +135,7 @@ class _Hookable(object):
             del self._post[name]
         else:
             raise KeyError('hook "{}" does not exist'.format(name))
+        _rules_version[0] += 1
 
     def has_hooks(self):
         return bool(self._pre) or bool(self._post)
@@ -112,6 +149,10 @@ class UpdateRule(object):
     """Base class of all update rules (``optimizer.py:148-530``)."""
 
     is_elementwise = False
+    _b200_versioned = True
+    enabled = _Tracked('enabled', True)
+    _use_fp32_update = _Tracked('use_fp32_update', False)
+    hyperparam = _Tracked('hyperparam', None)
 
     def __init__(self, parent_hyperparam=None):
         self._state = None
@@ -181,17 +222,19 @@ class UpdateRule(object):
         if self._state is not None:
             for key in self._state:
                 self._state[key] = serializer(key, self._state[key])
+        _rules_version[0] += 1      # state arrays may have been replaced
 
 
 class Optimizer(object):
     """Base class of all numerical optimizers (``optimizer.py:533-791``)."""
 
-    target = None
+    _b200_versioned = True
+    target = _Tracked('target', None)
     t = 0
     epoch = 0
-    _loss_scale = None
+    _loss_scale = _Tracked('loss_scale', None)
     _loss_scale_max = 65504
-    _loss_scaling_is_dynamic = False
+    _loss_scaling_is_dynamic = _Tracked('loss_scaling_is_dynamic', False)
     use_auto_new_epoch = False
 
     def __init__(self):

@@ -13,7 +13,7 @@ _table = [None]
 
 def single_param_table(param, states):
     """ParamsData of one parameter with `states` attached (ptr[2..])."""
-    if _table[0] is None:
+    if _table[0] is None or _table[0]._lib is not _lib.get():
         _table[0] = _mu.DeviceTable()
     return _mu.ParamsData([param], 'grad', False, extra_ptrs=[(param.data, list(states))],
                           table=_table[0])

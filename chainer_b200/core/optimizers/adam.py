@@ -116,6 +116,12 @@ class AdamRule(optimizer.UpdateRule):
     def fused_key(self):
         return ('adam',) + self.kernel_args()
 
+    def fused_signature(self):
+        """Grouping key that is defined before the first step (t == 0)."""
+        d = self.hyperparam.get_dict()
+        return ('adam', self.t, getattr(self, 'initial_alpha', None)) + \
+            tuple(sorted((k, float(v)) for k, v in d.items()))
+
     def update_core_gpu(self, param):
         grad = param.grad
         if grad is None:

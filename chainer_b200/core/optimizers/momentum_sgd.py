@@ -31,6 +31,9 @@ class MomentumSGDRule(optimizer.UpdateRule):
         hp = self.hyperparam
         return ('momentum_sgd', float(hp.lr), float(hp.momentum))
 
+    def fused_signature(self):
+        return self.fused_key() + (self.t,)
+
     def update_core_gpu(self, param):
         grad = param.grad
         if grad is None:

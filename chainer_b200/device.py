@@ -167,7 +167,8 @@ class Stream(object):
             self.ptr = int(ptr)
         else:
             p = ctypes.c_void_p()
-            _lib.get().gp_stream_create(ctypes.byref(p), 1 if non_blocking else 0)
+            self._lib = _lib.get()
+            self._lib.gp_stream_create(ctypes.byref(p), 1 if non_blocking else 0)
             self.ptr = p.value or 0
             self._owned = True
 
@@ -195,7 +196,7 @@ class Stream(object):
     def __del__(self):
         if getattr(self, '_owned', False) and self.ptr:
             try:
-                _lib.get().gp_stream_destroy(self.ptr)
+                self._lib.gp_stream_destroy(self.ptr)
             except Exception:
                 pass
 
@@ -221,7 +222,8 @@ def stream_ptr(stream):
 class Event(object):
     def __init__(self, timing=False):
         p = ctypes.c_void_p()
-        _lib.get().gp_event_create(ctypes.byref(p), 1 if timing else 0)
+        self._lib = _lib.get()
+        self._lib.gp_event_create(ctypes.byref(p), 1 if timing else 0)
         self.ptr = p.value
 
     def record(self, stream=None):
@@ -238,7 +240,7 @@ class Event(object):
     def __del__(self):
         if getattr(self, 'ptr', None):
             try:
-                _lib.get().gp_event_destroy(self.ptr)
+                self._lib.gp_event_destroy(self.ptr)
             except Exception:
                 pass
 
@@ -255,14 +257,15 @@ class _MemPtr(object):
 class _Allocation(object):
     def __init__(self, nbytes):
         p = ctypes.c_void_p()
-        _lib.get().gp_malloc(ctypes.byref(p), max(int(nbytes), 1))
+        self._lib = _lib.get()     # free with the library that allocated
+        self._lib.gp_malloc(ctypes.byref(p), max(int(nbytes), 1))
         self.ptr = p.value
         self.nbytes = nbytes
 
     def __del__(self):
         if getattr(self, 'ptr', None):
             try:
-                _lib.get().gp_free(self.ptr)
+                self._lib.gp_free(self.ptr)
             except Exception:
                 pass
             self.ptr = None

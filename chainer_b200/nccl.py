@@ -49,7 +49,8 @@ class NcclCommunicator(object):
     def __init__(self, ndev, commId, rank):
         _ensure_loaded()
         h = ctypes.c_void_p()
-        _lib.get().gp_nccl_comm_init_rank(ctypes.byref(h), ndev, bytes(commId), rank)
+        self._lib = _lib.get()
+        self._lib.gp_nccl_comm_init_rank(ctypes.byref(h), ndev, bytes(commId), rank)
         self.handle = h.value
         self.size = ndev
         self.rank = rank
@@ -65,7 +66,7 @@ class NcclCommunicator(object):
 
     def destroy(self):
         if self.handle:
-            _lib.get().gp_nccl_comm_destroy(self.handle)
+            self._lib.gp_nccl_comm_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -47,6 +47,14 @@ class _MultiNodeOptimizer(object):
             self.actual_optimizer.update(None, *args, **kwds)
 
     def is_changed(self, target):
+        # Fast path: Link classes that count structural changes
+        # (chainer_b200.core.link) need not be re-walked every step.
+        if getattr(target, '_b200_versioned', False):
+            from chainer_b200.core import link as _link
+            stamp = (id(target), _link.structure_version())
+            if self.__dict__.get('_stamp') == stamp:
+                return False
+            super(_MultiNodeOptimizer, self).__setattr__('_stamp', stamp)
         previous_params = self.target_params
         super(_MultiNodeOptimizer, self).__setattr__(
             'target_params', [(name, param.data is not None)

@@ -1,0 +1,149 @@
+"""Worker of tests/test_multi_gpu.py: one rank (one GPU) of a torchrun launch
+with the REAL library and NCCL.  Mirrors the reference's multi-rank tests
+(test_communicator.py:242-319, test_multi_node_optimizer.py:51-110,
+links_tests/test_batch_normalization.py:54-186)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def main():
+    rank = int(os.environ['RANK'])
+    world = int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import chainer_b200
+    from chainer_b200 import config
+    from chainer_b200.core.link import link_from_named_arrays
+    from oracle import gradpath as og
+
+    comm = chainer_b200.create_communicator('pure_nccl')
+    assert comm.size == world and comm.rank == rank and comm.intra_size == world
+
+    # ---- bcast_data + mean_grad analytic vectors -----------------------------
+    plist = [('/a/W', (3, 2)), ('/a/b', (3,)), ('/b/W', (4, 3)), ('/b/b', (4,)), ('/c/b', (5,))]
+    fills = [0, 0, 1, 1, 2]
+    model = link_from_named_arrays([(n, t(np.full(s, rank + k, np.float32)))
+                                    for (n, s), k in zip(plist, fills)])
+    comm.bcast_data(model)
+    for (_, p), k in zip(sorted(model.namedparams()), fills):
+        assert torch.equal(p.data, torch.full_like(p.data, k))
+    for adt in (None, np.float16, 'bfloat16'):
+        comm.set_config('allreduce_grad_dtype', adt)
+        for _ in range(2):
+            for (_, p), k in zip(sorted(model.namedparams()), fills):
+                p.grad = torch.full_like(p.data, rank + k)
+            comm.multi_node_mean_grad(model)
+            base = (world - 1.0) / 2
+            for (_, p), k in zip(sorted(model.namedparams()), fills):
+                np.testing.assert_allclose(p.grad.cpu().numpy(), base + k, rtol=1e-2 if adt else 1e-6)
+    comm.set_config('allreduce_grad_dtype', None)
+    # zero_fill on odd ranks (test_communicator.py:289-319)
+    for (_, p), k in zip(sorted(model.namedparams()), fills):
+        p.grad = torch.full_like(p.data, rank + k)
+    last = sorted(model.namedparams())[-1][1]
+    if rank % 2 == 1:
+        last.grad = None
+    comm.multi_node_mean_grad(model, zero_fill=True)
+    v = sum(i + 2 for i in range(world) if i % 2 == 0) / float(world)
+    np.testing.assert_allclose(last.grad.cpu().numpy(), v, rtol=1e-6)
+
+    # ---- fused multi-node optimizer vs oracle, bucketed -----------------------
+    from chainer_b200 import workloads
+    wl = workloads.scaled_histogram(600000)
+    for opt_name, adt, tol in (('momentum_sgd', None, 1e-6), ('adam', None, 1e-6),
+                               ('momentum_sgd', np.float16, 2e-3)):
+        comm.set_config('allreduce_grad_dtype', adt)
+        comm.bucket_bytes = 256 << 10                 # several buckets
+        rng = np.random.default_rng(7)
+        host_p = [(rng.standard_normal(s) * 0.05).astype(np.float32) for _, s in wl]
+        m = link_from_named_arrays([(n, t(a + rank)) for (n, _), a in zip(wl, host_p)])
+        actual = chainer_b200.MomentumSGD(lr=0.01) if opt_name == 'momentum_sgd' else chainer_b200.Adam()
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+        opt.setup(m)
+        opt.update()                                  # broadcast: rank 0's values everywhere
+        st = [dict(m=np.zeros_like(a), v=np.zeros_like(a)) for a in host_p]
+        for step in range(1, 4):
+            all_g = [[(np.random.default_rng(1000 * step + r).standard_normal(a.shape) * 1e-2)
+                      .astype(np.float32) for a in host_p] for r in range(world)]
+            for (_, p), g in zip(sorted(m.namedparams()), all_g[rank]):
+                p.grad = t(g)
+            opt.update()
+            torch.cuda.synchronize()
+            mean = og.multi_node_mean_grad(all_g, np.float32 if adt is None else adt)
+            for (name, p), q, g, s in zip(sorted(m.namedparams()), host_p, mean, st):
+                if opt_name == 'momentum_sgd':
+                    og.momentum_sgd_update(q, g, s['v'], 0.01, 0.9)
+                else:
+                    og.adam_update_gpu(q, g, s['m'], s['v'], step)
+                got = p.data.cpu().numpy()
+                if world == 2 and adt is None:
+                    assert np.array_equal(got, q), (opt_name, name, step)   # 2-rank sum is exact
+                else:
+                    np.testing.assert_allclose(got, q, rtol=tol, atol=tol * 1e-2)
+                np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=tol, atol=1e-8)
+            assert actual.t == step
+        # every rank holds identical parameters
+        flat = torch.cat([p.data.reshape(-1) for _, p in sorted(m.namedparams())])
+        ref = flat.clone().cpu()
+        parts = [torch.zeros_like(ref) for _ in range(world)]
+        dist.all_gather(parts, ref)
+        for prt in parts:
+            assert torch.equal(prt, ref)
+    comm.set_config('allreduce_grad_dtype', None)
+
+    # ---- debug mode across ranks ---------------------------------------------
+    config.set_debug(True)
+    for (_, p), k in zip(sorted(model.namedparams()), fills):
+        p.grad = torch.full_like(p.data, rank + k)
+    comm.multi_node_mean_grad(model)
+    if rank == 0:
+        sorted(model.namedparams())[0][1].grad[0, 0] = float('nan')
+    try:
+        comm.multi_node_mean_grad(model)
+        raise AssertionError('divergence not detected')
+    except ValueError as e:
+        assert 'diverged' in str(e)
+    config.set_debug(False)
+
+    # ---- MNBN: multi-worker == single worker on the global batch ---------------
+    from chainer_b200.links import MultiNodeBatchNormalization
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'mnbn.npz'))
+    if world == 2:
+        nb = 4
+        x = t(z['x'][rank * nb:(rank + 1) * nb]).requires_grad_(True)
+        C = z['gamma'].size
+        bn = MultiNodeBatchNormalization(C, comm)
+        bn.gamma.data.copy_(torch.from_numpy(z['gamma']))
+        bn.beta.data.copy_(torch.from_numpy(z['beta']))
+        bn.gamma.data.requires_grad_(True)
+        bn.beta.data.requires_grad_(True)
+        y = bn(x)
+        y.backward(t(z['gy'][rank * nb:(rank + 1) * nb]))
+        np.testing.assert_allclose(y.detach().cpu().numpy(), z['mn|%d|y' % rank], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), z['mn|%d|gx' % rank], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(bn.gamma.data.grad.cpu().numpy(), z['mn|%d|ggamma' % rank],
+                                   rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(bn.beta.data.grad.cpu().numpy(), z['mn|%d|gbeta' % rank],
+                                   rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(bn.avg_mean.cpu().numpy(), z['mn|%d|avg_mean' % rank],
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(bn.avg_var.cpu().numpy(), z['mn|%d|avg_var' % rank],
+                                   rtol=1e-4, atol=1e-6)
+    comm.finalize()
+    print('GPU RANK %d OK' % rank, flush=True)
+
+
+if __name__ == '__main__':
+    main()
