@@ -74,6 +74,10 @@ def test_multi_node_optimizer_fused_bit_exact(comm, opt_name, kw, pdtype, write_
     opt.setup(model)
     opt.update()
     assert actual.t == 0
+    # The first update() is bcast_data, whose transfer dtype is chainer.get_dtype()
+    # = float32 (pure_nccl_communicator.py:85-99): float64 parameters come back
+    # rounded to float32, exactly as in the reference.
+    host_p = [a.astype(np.float32).astype(pdtype) for a in host_p]
     st = [dict(m=np.zeros_like(a), v=np.zeros_like(a), vhat=np.zeros_like(a)) for a in host_p]
     for step in range(1, 4):
         grads = [np.asarray(rng.standard_normal(a.shape) * gscale).astype(pdtype).reshape(a.shape)
