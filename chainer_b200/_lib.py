@@ -74,10 +74,10 @@ PROTOTYPES = {
     'gp_unpack_scale': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                 c_double, c_void_p]),
     'gp_unpack_momentum_sgd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
-                                       c_int64, c_double, c_double, c_double, c_int, c_void_p]),
+                                       c_int64, c_double, c_double, c_double, c_int, c_int, c_void_p]),
     'gp_unpack_adam': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                c_double, c_double, c_double, c_double, c_double, c_double,
-                               c_double, c_double, c_double, c_int, c_int, c_void_p]),
+                               c_double, c_double, c_double, c_int, c_int, c_int, c_void_p]),
     'gp_scale': (c_int, [c_void_p, c_int, c_int64, c_double, c_void_p]),
     'gp_check_finite': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'gp_bn_workspace_bytes': (c_size_t, [c_int64]),

@@ -67,6 +67,7 @@ class ParamsData(object):
             segs['buf_off'] = csum[:-1]
         else:
             segs['buf_off'] = np.asarray(buf_offsets, dtype=np.int64)
+        self._hint4 = self._hint8 = False
         self.n_params = n_params
         self.n_elems = int(csum[n_params])
         self.attr_name = attr_name
@@ -109,6 +110,13 @@ class ParamsData(object):
         for k in range(1, 5):
             ok &= (segs['ptr'][:, k] % a1) == 0
         segs['flags'] = np.where(ok, _lib.GP_SEG_VEC_OK, 0).astype(np.uint32)
+        # layout promise for the TMA-staged kernels (include/gradpath.h "layout_hint"):
+        # uniform float32 arrays, 16-byte aligned pointers, offsets multiple of 8
+        # (of 4 when the packed buffer is a 4-byte type too)
+        f32 = bool(np.all(segs['dtype0'] == _lib.GP_F32) and np.all(segs['dtype1'] == _lib.GP_F32))
+        al16 = bool(np.all(segs['ptr'] % np.uint64(16) == 0))
+        self._hint4 = f32 and al16 and bool(np.all(csum % 4 == 0) and np.all(segs['buf_off'] % 4 == 0))
+        self._hint8 = self._hint4 and bool(np.all(csum % 8 == 0) and np.all(segs['buf_off'] % 8 == 0))
 
     def upload(self, stream=None):
         lib = _lib.get()
@@ -124,6 +132,14 @@ class ParamsData(object):
         self.d_segs = base + csum_bytes
         self._blob = blob
         return lib
+
+    def layout_hint(self, buf_dtype):
+        """layout_hint argument of the fused update kernels for this table."""
+        if self.n_params == 0:
+            return 0
+        four_byte = not isinstance(buf_dtype, str) and np.dtype(buf_dtype) == np.float32
+        ok = self._hint4 if four_byte else self._hint8
+        return _lib.GP_F32 if ok else 0
 
     # reference attribute names (device arrays there; device addresses here)
     @property

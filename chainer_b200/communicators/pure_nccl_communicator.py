@@ -515,13 +515,14 @@ class _FusedPlan(object):
             launches.append((key, t))
 
         def launch(key, t, begin, end):
+            hint = t.layout_hint(dtype)
             if key[0] == 'momentum_sgd':
                 lib.gp_unpack_momentum_sgd(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
-                                           begin, end, scale, key[1], key[2], wg, sp)
+                                           begin, end, scale, key[1], key[2], wg, hint, sp)
             else:
                 lib.gp_unpack_adam(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin, end,
                                    scale, key[1], key[2], key[3], key[4], key[5], key[6], key[7],
-                                   key[8], key[9], wg, sp)
+                                   key[8], key[9], wg, hint, sp)
 
         if len(launches) == 1:
             key0, t0 = launches[0]

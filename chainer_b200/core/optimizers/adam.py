@@ -135,7 +135,7 @@ class AdamRule(optimizer.UpdateRule):
         a = self.kernel_args()
         _lib.get().gp_unpack_adam(
             _dev.device_ptr(grad), _dev.dtype_id(_dev.array_dtype(grad)), pd.d_csum, pd.d_segs,
-            1, 0, pd.n_elems, 1.0, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], 0, 0)
+            1, 0, pd.n_elems, 1.0, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], 0, 0, 0)
 
 
 class Adam(optimizer.GradientMethod):

@@ -42,7 +42,7 @@ class MomentumSGDRule(optimizer.UpdateRule):
         pd = _single.single_param_table(param, [self.state['v']])
         _lib.get().gp_unpack_momentum_sgd(
             _dev.device_ptr(grad), _dev.dtype_id(_dev.array_dtype(grad)), pd.d_csum, pd.d_segs,
-            1, 0, pd.n_elems, 1.0, float(hp.lr), float(hp.momentum), 0, 0)
+            1, 0, pd.n_elems, 1.0, float(hp.lr), float(hp.momentum), 0, 0, 0)
 
 
 class MomentumSGD(optimizer.GradientMethod):

@@ -1,4 +1,4 @@
-// gp_update.cu -- fused unpack + descale + optimizer update.
+// gp_adam.cu -- fused unpack + descale + Adam-family update (see also gp_sgd.cu).
 //
 // Reference being replaced (chainer v7.8.1):
 //   K3 div_by_size              chainermn/communicators/pure_nccl_communicator.py:183-189
@@ -25,7 +25,7 @@
 // Algorithmic HBM bytes per element (fp32 params, buffer itemsize b):
 //   MomentumSGD  b + 8 (param r/w) + 8 (v r/w)  [+4 write_grad]
 //   Adam         b + 8 + 8 (m) + 8 (v)          [+4 write_grad] [+8 vhat]
-#include "gp_walk.cuh"
+#include "gp_bulk.cuh"
 
 namespace {
 
@@ -33,92 +33,11 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
   return reinterpret_cast<P*>(p);
 }
 
-// ------------------------------------------------------------ MomentumSGD --
-struct SgdOp {
-  static constexpr int kMaxUnroll = 4;
-  const void* buffer;
-  ScaleArg s;
-  double lr, momentum;
-  int write_grad;
-
-  static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype1; }
-
-  // one element, arithmetic in P exactly as update_core_cpu
-  // (momentum_sgd.py:61-73: v *= momentum; v -= lr * grad; param += v)
-  template <class P>
-  static __device__ __forceinline__ void math(typename Carrier<P>::type g,
-                                              typename Carrier<P>::type& p,
-                                              typename Carrier<P>::type& v,
-                                              typename Carrier<P>::type lr_,
-                                              typename Carrier<P>::type mom_) {
-    using A = Arith<P>;
-    v = A::sub(A::mul(mom_, v), A::mul(lr_, g));
-    p = A::add(p, v);
-  }
-
-  template <class B, class P, int U>
-  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
-                                      const bool (&act)[U]) const {
-    using CB = typename Carrier<B>::type;
-    using CP = typename Carrier<P>::type;
-    Raw4<B> rb[U];
-    Raw4<P> rp[U], rv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (act[u]) {
-        rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
-        rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
-        rv[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
-      }
-    }
-    const CP lr_ = Arith<P>::cst(lr), mom_ = Arith<P>::cst(momentum);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!act[u]) continue;
-      CB xb[4];
-      CP g[4], p[4], v[4];
-      unpack4(rb[u], xb);
-      unpack4(rp[u], p);
-      unpack4(rv[u], v);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        g[i] = gpw::mean_grad_value<B, P>(xb[i], s);
-        math<P>(g[i], p[i], v[i], lr_, mom_);
-      }
-      st4(mptr<P>(seg[u]->ptr[1]) + e[u], pack4<P, CP>(p));
-      st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, CP>(v));
-      if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
-    }
-  }
-
-  template <class B, class P>
-  __device__ __forceinline__ void one(const gp_seg_t& sg, int64_t e) const {
-    using CP = typename Carrier<P>::type;
-    const auto xb = to_carrier(reinterpret_cast<const B*>(buffer)[sg.buf_off + e]);
-    const CP g = gpw::mean_grad_value<B, P>(xb, s);
-    P* pp = mptr<P>(sg.ptr[1]) + e;
-    P* pv = mptr<P>(sg.ptr[2]) + e;
-    CP p = to_carrier(*pp), v = to_carrier(*pv);
-    math<P>(g, p, v, Arith<P>::cst(lr), Arith<P>::cst(momentum));
-    *pp = from_carrier<P>(p);
-    *pv = from_carrier<P>(v);
-    if (write_grad) mptr<P>(sg.ptr[0])[e] = from_carrier<P>(g);
-  }
-  template <class B>
-  __device__ __forceinline__ void scalar(const gp_seg_t& sg, int64_t e) const {
-    switch (sg.dtype1) {
-      case GP_F32: one<B, float>(sg, e); break;
-      case GP_F16: one<B, __half>(sg, e); break;
-      case GP_F64: one<B, double>(sg, e); break;
-      default: break;
-    }
-  }
-};
-
 // ------------------------------------------------------------------- Adam --
 template <class P> struct AdamT { using type = float; };
 template <> struct AdamT<double> { using type = double; };
 
+template <bool AMS>
 struct AdamOp {
   static constexpr int kMaxUnroll = 2;
   const void* buffer;
@@ -145,7 +64,7 @@ struct AdamOp {
     T m_ = I::add(m, I::mul(c.omb1, I::sub(g, m)));
     T v_ = I::add(v, I::mul(c.omb2, I::sub(I::mul(g, g), v)));
     T d_ = v_;
-    if (flags & GP_ADAM_AMSGRAD) {
+    if constexpr (AMS) {
       vh = I::max(vh, v_);
       d_ = vh;
     }
@@ -162,12 +81,12 @@ struct AdamOp {
     v = v_;
   }
 
-  template <class B, class P, int U>
+  template <class B, class P, int U, int SM>
   __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                       const bool (&act)[U]) const {
     using CB = typename Carrier<B>::type;
     using T = typename AdamT<P>::type;  // == Carrier<P>::type
-    const bool ams = flags & GP_ADAM_AMSGRAD;
+    constexpr bool ams = AMS;
     Raw4<B> rb[U];
     Raw4<P> rp[U], rm[U], rv[U], rh[U];
 #pragma unroll
@@ -177,7 +96,7 @@ struct AdamOp {
         rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
         rm[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
         rv[u] = ld4(mptr<P>(seg[u]->ptr[3]) + e[u]);
-        if (ams) rh[u] = ld4(mptr<P>(seg[u]->ptr[4]) + e[u]);
+        if constexpr (ams) rh[u] = ld4(mptr<P>(seg[u]->ptr[4]) + e[u]);
       }
     }
     const Consts<T> c = consts<T>();
@@ -190,74 +109,139 @@ struct AdamOp {
       unpack4(rp[u], p);
       unpack4(rm[u], m);
       unpack4(rv[u], v);
-      if (ams) unpack4(rh[u], vh);
+      if constexpr (ams) unpack4(rh[u], vh);
       else { vh[0] = vh[1] = vh[2] = vh[3] = (T)0; }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        g[i] = gpw::mean_grad_value<B, P>(xb[i], s);
+        g[i] = gpw::mean_grad_value<B, P, SM>(xb[i], s);
         math<P, T>(g[i], p[i], m[i], v[i], vh[i], c);
       }
       st4(mptr<P>(seg[u]->ptr[1]) + e[u], pack4<P, T>(p));
       st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, T>(m));
       st4(mptr<P>(seg[u]->ptr[3]) + e[u], pack4<P, T>(v));
-      if (ams) st4(mptr<P>(seg[u]->ptr[4]) + e[u], pack4<P, T>(vh));
+      if constexpr (ams) st4(mptr<P>(seg[u]->ptr[4]) + e[u], pack4<P, T>(vh));
       if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, T>(g));
     }
   }
 
-  template <class B, class P>
+  // TMA path: one tile, in place in shared memory (gp_bulk.cuh).
+  // arrays: 0 buffer, 1 param, 2 m, 3 v, [4 vhat,] last: grad out
+  template <class B, class P, int SM>
+  static __device__ __forceinline__ void tile(const AdamOp& op, unsigned char* st,
+                                              const gpb::BulkArgs& a, int n_vec) {
+    using CB = typename Carrier<B>::type;
+    using T = typename AdamT<P>::type;
+    B* sb = reinterpret_cast<B*>(st + a.arr[0].smem_off);
+    P* sp = reinterpret_cast<P*>(st + a.arr[1].smem_off);
+    P* sm = reinterpret_cast<P*>(st + a.arr[2].smem_off);
+    P* sv = reinterpret_cast<P*>(st + a.arr[3].smem_off);
+    P* sh = reinterpret_cast<P*>(st + a.arr[AMS ? 4 : 3].smem_off);
+    P* sg = reinterpret_cast<P*>(st + a.arr[AMS ? 5 : 4].smem_off);
+    const Consts<T> c = op.template consts<T>();
+    for (int v = threadIdx.x; v < n_vec; v += gpb::kConsumers) {
+      const Raw4<B> rb = gpb::lds4(sb + 4 * v);
+      const Raw4<P> rp = gpb::lds4(sp + 4 * v);
+      const Raw4<P> rm = gpb::lds4(sm + 4 * v);
+      const Raw4<P> rv = gpb::lds4(sv + 4 * v);
+      Raw4<P> rh;
+      if constexpr (AMS) rh = gpb::lds4(sh + 4 * v);
+      CB xb[4];
+      T g[4], p[4], m[4], vv[4], vh[4];
+      unpack4(rb, xb);
+      unpack4(rp, p);
+      unpack4(rm, m);
+      unpack4(rv, vv);
+      if constexpr (AMS) unpack4(rh, vh);
+      else { vh[0] = vh[1] = vh[2] = vh[3] = (T)0; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        g[i] = gpw::mean_grad_value<B, P, SM>(xb[i], op.s);
+        op.template math<P, T>(g[i], p[i], m[i], vv[i], vh[i], c);
+      }
+      gpb::sts4(sp + 4 * v, pack4<P, T>(p));
+      gpb::sts4(sm + 4 * v, pack4<P, T>(m));
+      gpb::sts4(sv + 4 * v, pack4<P, T>(vv));
+      if constexpr (AMS) gpb::sts4(sh + 4 * v, pack4<P, T>(vh));
+      if (op.write_grad) gpb::sts4(sg + 4 * v, pack4<P, T>(g));
+    }
+  }
+
+  template <class B, class P, int SM>
   __device__ __forceinline__ void one(const gp_seg_t& sg, int64_t e) const {
     using T = typename AdamT<P>::type;
-    const bool ams = flags & GP_ADAM_AMSGRAD;
+    constexpr bool ams = AMS;
     const auto xb = to_carrier(reinterpret_cast<const B*>(buffer)[sg.buf_off + e]);
-    const T g = gpw::mean_grad_value<B, P>(xb, s);
+    const T g = gpw::mean_grad_value<B, P, SM>(xb, s);
     P* pp = mptr<P>(sg.ptr[1]) + e;
     P* pm = mptr<P>(sg.ptr[2]) + e;
     P* pv = mptr<P>(sg.ptr[3]) + e;
     P* ph = mptr<P>(sg.ptr[4]) + e;
     T p = to_carrier(*pp), m = to_carrier(*pm), v = to_carrier(*pv);
-    T vh = ams ? (T)to_carrier(*ph) : (T)0;
+    T vh = (T)0;
+    if constexpr (ams) vh = (T)to_carrier(*ph);
     math<P, T>(g, p, m, v, vh, consts<T>());
     *pp = from_carrier<P>(p);
     *pm = from_carrier<P>(m);
     *pv = from_carrier<P>(v);
-    if (ams) *ph = from_carrier<P>(vh);
+    if constexpr (ams) *ph = from_carrier<P>(vh);
     if (write_grad) mptr<P>(sg.ptr[0])[e] = from_carrier<P>(g);
   }
-  template <class B>
+  template <class B, int SM>
   __device__ __forceinline__ void scalar(const gp_seg_t& sg, int64_t e) const {
     switch (sg.dtype1) {
-      case GP_F32: one<B, float>(sg, e); break;
-      case GP_F16: one<B, __half>(sg, e); break;
-      case GP_F64: one<B, double>(sg, e); break;
+      case GP_F32: one<B, float, SM>(sg, e); break;
+      case GP_F16: one<B, __half, SM>(sg, e); break;
+      case GP_F64: one<B, double, SM>(sg, e); break;
       default: break;
     }
   }
 };
 
-}  // namespace
-
-extern "C" int gp_unpack_momentum_sgd(const void* buffer, int buf_dtype, const int64_t* d_csum,
-                                      const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
-                                      int64_t elem_end, double scale, double lr, double momentum,
-                                      int write_grad, void* stream) {
-  SgdOp op;
+template <class Op>
+void fill_adam(Op& op, const void* buffer, double scale, double alpha_t, double omb1, double omb2,
+               double eps, double eta, double wd, double lower, double upper, int flags,
+               int write_grad) {
   op.buffer = buffer;
   op.s = make_scale(scale);
-  op.lr = lr;
-  op.momentum = momentum;
-  op.write_grad = write_grad;
-  return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                         "gp_unpack_momentum_sgd");
+  op.alpha_t = alpha_t; op.omb1 = omb1; op.omb2 = omb2; op.eps = eps; op.eta = eta; op.wd = wd;
+  op.lower = lower; op.upper = upper; op.flags = flags; op.write_grad = write_grad;
 }
+
+}  // namespace
 
 extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* d_csum,
                               const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
                               int64_t elem_end, double scale, double alpha_t,
                               double one_minus_beta1, double one_minus_beta2, double eps,
                               double eta, double weight_decay_rate, double lower, double upper,
-                              int adam_flags, int write_grad, void* stream) {
-  AdamOp op;
+                              int adam_flags, int write_grad, int layout_hint, void* stream) {
+  gpb::BulkArgs a = {};
+  if (layout_hint && n_segs > 0) {
+    a.csum = d_csum; a.segs = d_segs; a.n_segs = n_segs; a.begin = elem_begin; a.end = elem_end;
+    a.buffer = buffer;
+    const int ps = gp_itemsize(layout_hint);
+    const bool ams = adam_flags & GP_ADAM_AMSGRAD;
+    int q = 0;
+    a.arr[q++] = {-1, 0, 1, 0, 0};          // packed buffer
+    a.arr[q++] = {1, ps, 1, 1, 0};          // param
+    a.arr[q++] = {2, ps, 1, 1, 0};          // m
+    a.arr[q++] = {3, ps, 1, 1, 0};          // v
+    if (ams) a.arr[q++] = {4, ps, 1, 1, 0}; // vhat
+    a.arr[q] = {0, ps, 0, 1, 0};            // mean gradient written back
+    a.n_arrays = write_grad ? q + 1 : q;
+  }
+  if (adam_flags & GP_ADAM_AMSGRAD) {
+    AdamOp<true> op;
+    fill_adam(op, buffer, scale, alpha_t, one_minus_beta1, one_minus_beta2, eps, eta,
+              weight_decay_rate, lower, upper, adam_flags, write_grad);
+    if (layout_hint && n_segs > 0) {
+      const int r = gpb::launch_bulk(buf_dtype, layout_hint, a, op, stream, "gp_unpack_adam");
+      if (r <= 0) return r;
+    }
+    return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
+                           "gp_unpack_adam");
+  }
+  AdamOp<false> op;
   op.buffer = buffer;
   op.s = make_scale(scale);
   op.alpha_t = alpha_t;
@@ -270,6 +254,10 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
   op.upper = upper;
   op.flags = adam_flags;
   op.write_grad = write_grad;
+  if (layout_hint && n_segs > 0) {
+    const int r = gpb::launch_bulk(buf_dtype, layout_hint, a, op, stream, "gp_unpack_adam");
+    if (r <= 0) return r;
+  }
   return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
                          "gp_unpack_adam");
 }

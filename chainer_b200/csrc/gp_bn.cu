@@ -195,8 +195,8 @@ __global__ void bn_finish_kernel(T* buf, int64_t C, ScaleArg s, T* var) {
   using A = Arith<T>;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const auto m = descale<T>(to_carrier(buf[c]), s);
-  const auto q = descale<T>(to_carrier(buf[C + c]), s);
+  const auto m = descale_rt<T>(to_carrier(buf[c]), s);
+  const auto q = descale_rt<T>(to_carrier(buf[C + c]), s);
   buf[c] = from_carrier<T>(m);
   buf[C + c] = from_carrier<T>(q);
   var[c] = from_carrier<T>(A::sub(q, A::mul(m, m)));

@@ -103,19 +103,31 @@ inline ScaleArg make_scale(double s) {
   return a;
 }
 
-// value read from a buffer of type B (as carrier) -> scaled, rounded to B
-template <class B>
+// value read from a buffer of type B (as carrier) -> scaled, rounded to B.
+// The mode is a compile-time parameter of the kernels: with a run-time switch
+// the compiler evaluated the double path speculatively for every element.
+template <class B, int SM>
 __device__ __forceinline__ typename Carrier<B>::type descale(typename Carrier<B>::type x,
                                                              const ScaleArg& s) {
-  if (s.mode == 0) return x;
-  if (s.mode == 1) {
+  if constexpr (SM == 0) {
+    return x;
+  } else if constexpr (SM == 1) {
     if constexpr (sizeof(typename Carrier<B>::type) == 8) {
       return __dmul_rn(x, s.ds);
     } else {
       return round_through<B>(__fmul_rn(x, s.fs));
     }
+  } else {
+    return round_through<B>(__dmul_rn((double)x, s.ds));
   }
-  return round_through<B>(__dmul_rn((double)x, s.ds));
+}
+// run-time mode (small flat kernels only)
+template <class B>
+__device__ __forceinline__ typename Carrier<B>::type descale_rt(typename Carrier<B>::type x,
+                                                                const ScaleArg& s) {
+  if (s.mode == 0) return descale<B, 0>(x, s);
+  if (s.mode == 1) return descale<B, 1>(x, s);
+  return descale<B, 2>(x, s);
 }
 
 // ------------------------------------------------------- 4-wide accessors --

@@ -27,23 +27,25 @@ struct PackOp {
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
 
-  template <class B, class P, class CP>
+  // (B)(scale * x): product in double (or exactly in float for 2^k), ONE rounding
+  template <class B, int SM, class CP>
   __device__ __forceinline__ Raw4<B> convert(const CP (&x)[4]) const {
-    if (s.mode == 2 || (s.mode == 1 && sizeof(CP) == 8)) {
+    if constexpr (SM == 2 || (SM == 1 && sizeof(CP) == 8)) {
       double y[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[i] = __dmul_rn((double)x[i], s.ds);
       return pack4<B, double>(y);
-    } else if (s.mode == 1) {
+    } else if constexpr (SM == 1) {
       float y[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[i] = __fmul_rn((float)x[i], s.fs);  // exact: factor is 2^k
       return pack4<B, float>(y);
+    } else {
+      return pack4<B, CP>(x);
     }
-    return pack4<B, CP>(x);
   }
 
-  template <class B, class P, int U>
+  template <class B, class P, int U, int SM>
   __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                       const bool (&act)[U]) const {
     using CP = typename Carrier<P>::type;
@@ -56,26 +58,26 @@ struct PackOp {
       if (!act[u]) continue;
       CP x[4];
       unpack4(in[u], x);
-      st4(reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u], convert<B, P, CP>(x));
+      st4(reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u], convert<B, SM, CP>(x));
     }
   }
 
-  template <class B, class P>
+  template <class B, class P, int SM>
   __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
     using CP = typename Carrier<P>::type;
     const CP x = to_carrier(cptr<P>(g.ptr[0])[e]);
     B out;
-    if (s.mode == 2 || (s.mode == 1 && sizeof(CP) == 8)) out = from_d<B>(__dmul_rn((double)x, s.ds));
-    else if (s.mode == 1) out = from_f<B>(__fmul_rn((float)x, s.fs));
+    if constexpr (SM == 2 || (SM == 1 && sizeof(CP) == 8)) out = from_d<B>(__dmul_rn((double)x, s.ds));
+    else if constexpr (SM == 1) out = from_f<B>(__fmul_rn((float)x, s.fs));
     else out = from_carrier<B>(x);
     reinterpret_cast<B*>(buffer)[g.buf_off + e] = out;
   }
-  template <class B>
+  template <class B, int SM>
   __device__ __forceinline__ void scalar(const gp_seg_t& g, int64_t e) const {
     switch (g.dtype0) {
-      case GP_F32: one<B, float>(g, e); break;
-      case GP_F16: one<B, __half>(g, e); break;
-      case GP_F64: one<B, double>(g, e); break;
+      case GP_F32: one<B, float, SM>(g, e); break;
+      case GP_F16: one<B, __half, SM>(g, e); break;
+      case GP_F64: one<B, double, SM>(g, e); break;
       default: break;
     }
   }
@@ -89,7 +91,7 @@ struct UnpackOp {
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
 
-  template <class B, class P, int U>
+  template <class B, class P, int U, int SM>
   __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                       const bool (&act)[U]) const {
     using CB = typename Carrier<B>::type;
@@ -105,21 +107,21 @@ struct UnpackOp {
       CP g[4];
       unpack4(in[u], x);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) g[i] = gpw::mean_grad_value<B, P>(x[i], s);
+      for (int i = 0; i < 4; ++i) g[i] = gpw::mean_grad_value<B, P, SM>(x[i], s);
       st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
     }
   }
-  template <class B, class P>
+  template <class B, class P, int SM>
   __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
     const auto x = to_carrier(reinterpret_cast<const B*>(buffer)[g.buf_off + e]);
-    mptr<P>(g.ptr[0])[e] = from_carrier<P>(gpw::mean_grad_value<B, P>(x, s));
+    mptr<P>(g.ptr[0])[e] = from_carrier<P>(gpw::mean_grad_value<B, P, SM>(x, s));
   }
-  template <class B>
+  template <class B, int SM>
   __device__ __forceinline__ void scalar(const gp_seg_t& g, int64_t e) const {
     switch (g.dtype0) {
-      case GP_F32: one<B, float>(g, e); break;
-      case GP_F16: one<B, __half>(g, e); break;
-      case GP_F64: one<B, double>(g, e); break;
+      case GP_F32: one<B, float, SM>(g, e); break;
+      case GP_F16: one<B, __half, SM>(g, e); break;
+      case GP_F64: one<B, double, SM>(g, e); break;
       default: break;
     }
   }
@@ -134,12 +136,12 @@ __global__ void __launch_bounds__(256) scale_kernel(B* __restrict__ buf, int64_t
     typename Carrier<B>::type x[4];
     unpack4(ld4(buf + 4 * i), x);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = descale<B>(x[k], s);
+    for (int k = 0; k < 4; ++k) x[k] = descale_rt<B>(x[k], s);
     st4(buf + 4 * i, pack4<B, typename Carrier<B>::type>(x));
   }
   // tail (< 4 elements)
   const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) buf[t] = from_carrier<B>(descale<B>(to_carrier(buf[t]), s));
+  if (t < n) buf[t] = from_carrier<B>(descale_rt<B>(to_carrier(buf[t]), s));
 }
 
 __device__ __forceinline__ bool is_finite_c(float x) { return isfinite(x); }

@@ -10,7 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "gp_common.cuh"
+#include "gp_bulk.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -30,6 +30,8 @@ int gp_cuda_fail(cudaError_t e, const char* what) {
 // defaults: see DESIGN.md "tuning"
 GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 4, /*ctas_per_sm*/ 8, /*persistent*/ 1,
                         /*bn_threads*/ 256};
+
+gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 1, /*tile*/ 2048, /*stages*/ 4};
 
 int gp_sm_count_cached() {
   static thread_local int cached_dev = -1;
@@ -58,6 +60,9 @@ int gp_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "ctas_per_sm")) g_gp_tuning.ctas_per_sm = value;
   else if (!strcmp(key, "persistent")) g_gp_tuning.persistent = value;
   else if (!strcmp(key, "bn_threads")) g_gp_tuning.bn_threads = value;
+  else if (!strcmp(key, "bulk")) gpb::g_bulk_tuning.enable = value;
+  else if (!strcmp(key, "bulk_tile")) gpb::g_bulk_tuning.tile = value < 512 ? 512 : (value & ~511);
+  else if (!strcmp(key, "bulk_stages")) gpb::g_bulk_tuning.stages = value < 2 ? 2 : value;
   else {
     gp_set_error("gp_set_tuning: unknown key '%s'", key);
     return GP_EINVAL;
@@ -71,6 +76,9 @@ int gp_get_tuning(const char* key, int* value) {
   else if (!strcmp(key, "ctas_per_sm")) *value = g_gp_tuning.ctas_per_sm;
   else if (!strcmp(key, "persistent")) *value = g_gp_tuning.persistent;
   else if (!strcmp(key, "bn_threads")) *value = g_gp_tuning.bn_threads;
+  else if (!strcmp(key, "bulk")) *value = gpb::g_bulk_tuning.enable;
+  else if (!strcmp(key, "bulk_tile")) *value = gpb::g_bulk_tuning.tile;
+  else if (!strcmp(key, "bulk_stages")) *value = gpb::g_bulk_tuning.stages;
   else {
     gp_set_error("gp_get_tuning: unknown key '%s'", key);
     return GP_EINVAL;

@@ -56,10 +56,11 @@ __device__ __forceinline__ int seg_seek(const int64_t* cs, int n, int j, int64_t
 
 // An Op supplies
 //   static int key(const gp_seg_t&)          dtype id a vector tile must agree on
-//   template <class B, class P, int U> void vec(seg[U], e[U], act[U]) const
-//   template <class B> void scalar(const gp_seg_t&, int64_t e) const
+//   ScaleArg s                               (s.mode selects the SM instantiation)
+//   template <class B, class P, int U, int SM> void vec(seg[U], e[U], act[U]) const
+//   template <class B, int SM> void scalar(const gp_seg_t&, int64_t e) const
 // B = buffer element type (per launch), P = parameter element type (per tile).
-template <class Op, class B, int U>
+template <class Op, class B, int U, int SM>
 __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, const Op op) {
   extern __shared__ int64_t s_csum[];
   const int n = a.n_segs;
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
 
     if (ok) {
       switch (my_key) {
-        case GP_F32: op.template vec<B, float, U>(sg, e, act); break;
-        case GP_F16: op.template vec<B, __half, U>(sg, e, act); break;
+        case GP_F32: op.template vec<B, float, U, SM>(sg, e, act); break;
+        case GP_F16: op.template vec<B, __half, U, SM>(sg, e, act); break;
         default: break;
       }
     } else {
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
         const int64_t flat = base + (int64_t)k * 32 + lane;
         if (flat < hi) {
           js = seg_seek(cs, n, js, flat);
-          op.template scalar<B>(a.segs[js], flat - cs[js]);
+          op.template scalar<B, SM>(a.segs[js], flat - cs[js]);
         }
       }
     }
@@ -142,13 +143,13 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
 
 // resident CTAs per SM of one instantiation (cached: the occupancy query is a
 // host-side calculation but not free)
-template <class Op, class B, int U>
+template <class Op, class B, int U, int SM>
 int resident_ctas(int threads, size_t smem) {
   static int c_threads = -1, c_occ = 1;
   static size_t c_smem = 0;
   if (threads != c_threads || smem != c_smem) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U>, threads, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U, SM>, threads, smem) !=
             cudaSuccess || occ < 1) {
       (void)cudaGetLastError();
       occ = 1;
@@ -160,7 +161,7 @@ int resident_ctas(int threads, size_t smem) {
   return c_occ;
 }
 
-template <class Op, class B, int U>
+template <class Op, class B, int U, int SM>
 int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st, const char* what) {
   const GpTuning& t = g_gp_tuning;
   const int64_t total = a.end - a.begin;
@@ -169,7 +170,7 @@ int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st
   if (t.persistent) {
     // every CTA must be resident at once, otherwise the equal slices would run
     // in waves: cap the grid by the real occupancy of this instantiation.
-    int per_sm = resident_ctas<Op, B, U>(threads, smem);
+    int per_sm = resident_ctas<Op, B, U, SM>(threads, smem);
     if (t.ctas_per_sm > 0 && t.ctas_per_sm < per_sm) per_sm = t.ctas_per_sm;
     const int64_t max_grid = (int64_t)gp_sm_count_cached() * per_sm;
     grid = (total + cta_tile - 1) / cta_tile;
@@ -186,7 +187,7 @@ int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st
     gp_set_error("%s: grid too large", what);
     return GP_EINVAL;
   }
-  walk_kernel<Op, B, U><<<(unsigned)grid, threads, smem, st>>>(a, op);
+  walk_kernel<Op, B, U, SM><<<(unsigned)grid, threads, smem, st>>>(a, op);
   return gp_cuda_fail(cudaGetLastError(), what);
 }
 
@@ -205,7 +206,7 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
   if (threads < 32) threads = 32;
   if (threads > kMaxThreads) threads = kMaxThreads;
   threads &= ~31;
-  int U = t.unroll >= 4 ? 4 : (t.unroll >= 2 ? 2 : 1);
+  int U = t.unroll >= 4 ? 4 : 2;
   if (sizeof(B) == 8 && U > 2) U = 2;
   if (U > Op::kMaxUnroll) U = Op::kMaxUnroll;
 
@@ -220,11 +221,16 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
   const size_t smem = a.use_smem ? (size_t)(n_segs + 1) * sizeof(int64_t) : 0;
 
   cudaStream_t st = (cudaStream_t)stream;
-  switch (U) {
-    case 4: return launch_u<Op, B, 4>(a, op, threads, smem, st, what);
-    case 2: return launch_u<Op, B, 2>(a, op, threads, smem, st, what);
-    default: return launch_u<Op, B, 1>(a, op, threads, smem, st, what);
+  const int mode = op.s.mode;
+#define GP_LAUNCH(UU)                                                              \
+  switch (mode) {                                                                  \
+    case 0: return launch_u<Op, B, UU, 0>(a, op, threads, smem, st, what);         \
+    case 1: return launch_u<Op, B, UU, 1>(a, op, threads, smem, st, what);         \
+    default: return launch_u<Op, B, UU, 2>(a, op, threads, smem, st, what);        \
   }
+  if (U >= 4) { GP_LAUNCH(4) }
+  GP_LAUNCH(2)
+#undef GP_LAUNCH
 }
 
 // dispatch on the runtime buffer dtype
@@ -245,10 +251,10 @@ int launch_buf(int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs, int
 // value of the packed buffer (type B, as carrier) -> mean gradient in the
 // parameter's type P (as carrier): descale, round to B (the reference scales the
 // buffer in place), then cast to P (unpack kernel, _memory_utility.py:392-425).
-template <class B, class P>
+template <class B, class P, int SM>
 __device__ __forceinline__ typename Carrier<P>::type mean_grad_value(
     typename Carrier<B>::type x, const ScaleArg& s) {
-  return round_through<P>(descale<B>(x, s));
+  return round_through<P>(descale<B, SM>(x, s));
 }
 
 }  // namespace gpw

@@ -148,6 +148,13 @@ int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
                     double scale, void* stream);
 
 /*
+ * layout_hint (fused update kernels): 0 = no promise (register-path kernel);
+ * GP_F32 = the caller guarantees that every segment has dtype0 == dtype1 ==
+ * float32, every pointer is 16-byte aligned and every csum / buf_off value is a
+ * multiple of 8 elements (4 suffices with a 4-byte buffer dtype).  The library
+ * then uses the TMA-staged kernel (gp_bulk.cuh): 1-D bulk copies into a ring of
+ * shared-memory stages, arithmetic from shared memory, bulk stores back.
+ *
  * gp_unpack_momentum_sgd: fused unpack + descale + MomentumSGD update.
  *   g = (dtype0)((buf_dtype)(scale * buffer[buf_off + k]))
  *   v = momentum * v - lr * g ;  param += v        (arithmetic in dtype1)
@@ -160,7 +167,7 @@ int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
 int gp_unpack_momentum_sgd(const void* buffer, int buf_dtype, const int64_t* d_csum,
                            const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
                            int64_t elem_end, double scale, double lr, double momentum,
-                           int write_grad, void* stream);
+                           int write_grad, int layout_hint, void* stream);
 
 /*
  * gp_unpack_adam: fused unpack + descale + Adam / AdamW / AMSGrad / AdaBound.
@@ -176,7 +183,8 @@ int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* d_csum,
                    const gp_seg_t* d_segs, int n_segs, int64_t elem_begin, int64_t elem_end,
                    double scale, double alpha_t, double one_minus_beta1,
                    double one_minus_beta2, double eps, double eta, double weight_decay_rate,
-                   double lower, double upper, int adam_flags, int write_grad, void* stream);
+                   double lower, double upper, int adam_flags, int write_grad, int layout_hint,
+                   void* stream);
 
 /* gp_scale: buffer[k] = (dtype)(buffer[k] * scale), in place.  Replaces the
  * `div_by_size` ElementwiseKernel (pure_nccl_communicator.py:183-189) where it

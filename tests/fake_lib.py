@@ -214,7 +214,7 @@ class FakeLib(object):
         return 0
 
     def gp_unpack_momentum_sgd(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, lr,
-                               momentum, write_grad, stream):
+                               momentum, write_grad, layout_hint, stream):
         self.calls.append(('gp_unpack_momentum_sgd', (buf_dtype, n, begin, end, scale, lr, momentum,
                                                       write_grad)))
         csum, segs = self._tables_of(d_csum, d_segs, n)
@@ -230,7 +230,7 @@ class FakeLib(object):
         return 0
 
     def gp_unpack_adam(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, alpha_t,
-                       omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad, stream):
+                       omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad, layout_hint, stream):
         self.calls.append(('gp_unpack_adam', (buf_dtype, n, begin, end, scale, alpha_t, flags,
                                               write_grad)))
         csum, segs = self._tables_of(d_csum, d_segs, n)

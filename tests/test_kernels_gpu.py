@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 BUF_DTYPES = ['float32', 'float16', 'bfloat16', 'float64']
 RAGGED = [7, 1, 0, 1000, 4096, 12345, 64, 3, 513, 2048, 70001]
 ALIGNED = [64, 64, 9408, 64, 2048, 1000, 256, 16384, 36864, 4, 131072]
+ALIGNED8 = [64, 8, 9408, 64, 2048, 1000, 256, 16384, 36864, 8, 131072, 0, 24, 70000]
 
 
 def _torch_buf(n, dtype):
@@ -46,19 +47,28 @@ class _Buf(object):
         return self.t.data_ptr()
 
 
-@pytest.fixture(params=[(256, 4, 1), (128, 1, 1), (512, 2, 0), (256, 4, 0)],
-                ids=['t256u4p', 't128u1p', 't512u2np', 't256u4np'])
+@pytest.fixture(params=[(256, 4, 1, 1, 2048, 4), (128, 1, 1, 0, 2048, 4), (512, 2, 0, 1, 512, 2),
+                        (256, 4, 0, 1, 4096, 3)],
+                ids=['t256u4p-bulk', 't128u1p-nobulk', 't512u2np-bulk512x2', 't256u4np-bulk4096x3'])
 def tuning(request):
+    """(threads, unroll, persistent) of the register-path walker and
+    (enable, tile, stages) of the TMA-staged kernels."""
     from chainer_b200 import _lib
     lib = _lib.get()
-    threads, unroll, persistent = request.param
+    threads, unroll, persistent, bulk, tile, stages = request.param
     lib.gp_set_tuning(b'threads', threads)
     lib.gp_set_tuning(b'unroll', unroll)
     lib.gp_set_tuning(b'persistent', persistent)
+    lib.gp_set_tuning(b'bulk', bulk)
+    lib.gp_set_tuning(b'bulk_tile', tile)
+    lib.gp_set_tuning(b'bulk_stages', stages)
     yield request.param
     lib.gp_set_tuning(b'threads', 256)
     lib.gp_set_tuning(b'unroll', 4)
     lib.gp_set_tuning(b'persistent', 1)
+    lib.gp_set_tuning(b'bulk', 1)
+    lib.gp_set_tuning(b'bulk_tile', 2048)
+    lib.gp_set_tuning(b'bulk_stages', 4)
 
 
 @pytest.mark.parametrize('buf_dtype', BUF_DTYPES)
@@ -121,7 +131,7 @@ def _states(host_params, names):
 @pytest.mark.parametrize('buf_dtype', ['float32', 'float16', 'bfloat16'])
 @pytest.mark.parametrize('sizes,pdtype', [(ALIGNED, 'float32'), (RAGGED, 'float32'),
                                           (ALIGNED, 'float16'), (RAGGED, 'float64'),
-                                          (RAGGED, 'float16')])
+                                          (RAGGED, 'float16'), (ALIGNED8, 'float32')])
 @pytest.mark.parametrize('n_ranks', [1, 8, 3])
 @pytest.mark.parametrize('write_grad', [0, 1])
 def test_fused_momentum_sgd_bit_exact(buf_dtype, sizes, pdtype, n_ranks, write_grad, tuning):
@@ -149,7 +159,7 @@ def test_fused_momentum_sgd_bit_exact(buf_dtype, sizes, pdtype, n_ranks, write_g
                            extra_ptrs=[(d_p[i], [d_v[i]]) for i in range(len(sizes))])
         lib.gp_unpack_momentum_sgd(buf.data_ptr(), dev.dtype_id(_odt(buf_dtype)), pd.d_csum,
                                    pd.d_segs, pd.n_params, 0, n, 1.0 / n_ranks, lr, mom,
-                                   write_grad, 0)
+                                   write_grad, pd.layout_hint(_odt(buf_dtype)), 0)
         torch.cuda.synchronize()
         g = og.mean_grad_value(summed, _odt(buf_dtype), n_ranks, pdt)
         cs = og.size_csum(hp)
@@ -175,7 +185,8 @@ ADAM_VARIANTS = {
 
 @pytest.mark.parametrize('buf_dtype', ['float32', 'float16'])
 @pytest.mark.parametrize('sizes,pdtype', [(ALIGNED, 'float32'), (RAGGED, 'float32'),
-                                          (ALIGNED, 'float16'), (RAGGED, 'float64')])
+                                          (ALIGNED, 'float16'), (RAGGED, 'float64'),
+                                          (ALIGNED8, 'float32')])
 @pytest.mark.parametrize('variant', sorted(ADAM_VARIANTS))
 def test_fused_adam_bit_exact(buf_dtype, sizes, pdtype, variant, tuning):
     import torch
@@ -212,7 +223,7 @@ def test_fused_adam_bit_exact(buf_dtype, sizes, pdtype, variant, tuning):
         lib.gp_unpack_adam(buf.data_ptr(), dev.dtype_id(_odt(buf_dtype)), pd.d_csum, pd.d_segs,
                            pd.n_params, 0, n, 1.0 / n_ranks, alpha_t, 1 - kw['beta1'],
                            1 - kw['beta2'], kw['eps'], kw['eta'], kw['weight_decay_rate'],
-                           lower, upper, flags, 1, 0)
+                           lower, upper, flags, 1, pd.layout_hint(_odt(buf_dtype)), 0)
         torch.cuda.synchronize()
         g = og.mean_grad_value(summed, _odt(buf_dtype), n_ranks, pdt)
         cs = og.size_csum(hp)
@@ -282,8 +293,9 @@ def test_resnet50_full_size_roundtrip_and_update():
     flat = torch.cat(grads)
     assert torch.equal(buf, flat)                     # layout: bit-exact
     want_p = [d - 0.01 * (g * 0.125) for d, g in zip(data, grads)]
+    assert pd.layout_hint(np.float32) == 7          # ResNet-50 takes the TMA-staged kernel
     lib.gp_unpack_momentum_sgd(buf.data_ptr(), 7, pd.d_csum, pd.d_segs, pd.n_params, 0, n,
-                               0.125, 0.01, 0.9, 1, 0)
+                               0.125, 0.01, 0.9, 1, 7, 0)
     torch.cuda.synchronize()
     for g, g0 in zip(grads, torch.split(flat, [x.numel() for x in grads])):
         assert torch.equal(g, g0 * 0.125)             # written-back mean gradient

@@ -49,6 +49,8 @@ def main():
     pd_adam = mu.ParamsData(params, 'grad', False,
                             extra_ptrs=[(d, [x, y]) for d, x, y in zip(data, m, v)])
     torch.cuda.synchronize()
+    bnp = {'float32': np.float32, 'float16': np.float16, 'bfloat16': 'bfloat16'}[args.buf]
+    hint = pd_sgd.layout_hint(bnp)
     for kind in args.kinds.split(','):
         for _ in range(args.reps):
             flush.zero_()        # evict L2 between launches (a vectorized fill, not walk_kernel)
@@ -60,11 +62,11 @@ def main():
             elif kind in ('sgd', 'sgd_wg'):
                 lib.gp_unpack_momentum_sgd(buf.data_ptr(), bid, pd_sgd.d_csum, pd_sgd.d_segs,
                                            len(sizes), 0, n, 0.125, 0.01, 0.9,
-                                           1 if kind == 'sgd_wg' else 0, 0)
+                                           1 if kind == 'sgd_wg' else 0, hint, 0)
             elif kind in ('adam', 'adam_wg'):
                 lib.gp_unpack_adam(buf.data_ptr(), bid, pd_adam.d_csum, pd_adam.d_segs, len(sizes), 0,
                                    n, 0.125, 1e-3, 0.1, 0.001, 1e-8, 1.0, 0.0, 0.0, 0.0, 0,
-                                   1 if kind == 'adam_wg' else 0, 0)
+                                   1 if kind == 'adam_wg' else 0, hint, 0)
             torch.cuda.synchronize()
     print('done', args.kinds)
 

@@ -42,6 +42,7 @@ def main():
     ap.add_argument('--sets', type=int, default=3)
     ap.add_argument('--out', default='gpurun_out/sweep.json')
     ap.add_argument('--quick', action='store_true')
+    ap.add_argument('--bulk-sweep', action='store_true', help='sweep the TMA-staged kernels (tile, stages)')
     args = ap.parse_args()
     lib = _lib.get()
     plist = workloads.WORKLOADS[args.workload]()
@@ -65,7 +66,10 @@ def main():
         sets.append(dict(buf=buf, pd_sgd=pd_sgd, pd_adam=pd_adam, keep=(grads, data, m, v, params)))
     torch.cuda.synchronize()
 
+    bnp = {'float32': np.float32, 'float16': np.float16, 'bfloat16': 'bfloat16'}[args.buf]
+
     def run(kind, st):
+        hint = st['pd_sgd'].layout_hint(bnp)
         if kind == 'pack':
             lib.gp_pack(st['buf'].data_ptr(), bid, st['pd_sgd'].d_csum, st['pd_sgd'].d_segs,
                         len(sizes), 0, n, 1.0, 0)
@@ -75,11 +79,11 @@ def main():
         elif kind in ('sgd', 'sgd_wg'):
             lib.gp_unpack_momentum_sgd(st['buf'].data_ptr(), bid, st['pd_sgd'].d_csum,
                                        st['pd_sgd'].d_segs, len(sizes), 0, n, 0.125, 0.01, 0.9,
-                                       1 if kind == 'sgd_wg' else 0, 0)
+                                       1 if kind == 'sgd_wg' else 0, hint, 0)
         elif kind in ('adam', 'adam_wg'):
             lib.gp_unpack_adam(st['buf'].data_ptr(), bid, st['pd_adam'].d_csum, st['pd_adam'].d_segs,
                                len(sizes), 0, n, 0.125, 1e-3, 0.1, 0.001, 1e-8, 1.0, 0.0, 0.0, 0.0,
-                               0, 1 if kind == 'adam_wg' else 0, 0)
+                               0, 1 if kind == 'adam_wg' else 0, hint, 0)
 
     bytes_per_elem = {'pack': 4 + bsz, 'unpack': bsz + 4, 'sgd': bsz + 16, 'sgd_wg': bsz + 20,
                       'adam': bsz + 24, 'adam_wg': bsz + 28}
@@ -110,6 +114,22 @@ def main():
             list(itertools.product([128, 256, 512], [1, 2, 4], [0], [0]))
     results = []
     kinds = ['pack', 'unpack', 'sgd', 'sgd_wg', 'adam', 'adam_wg']
+    if args.bulk_sweep:
+        kinds = ['sgd', 'sgd_wg', 'adam', 'adam_wg']
+        for bulk, tile, stages in [(0, 2048, 4)] + [(1, t, s) for t in (1024, 2048, 4096) for s in (2, 3, 4, 6)]:
+            lib.gp_set_tuning(b'bulk', bulk)
+            lib.gp_set_tuning(b'bulk_tile', tile)
+            lib.gp_set_tuning(b'bulk_stages', stages)
+            row = dict(bulk=bulk, tile=tile, stages=stages)
+            msg = 'bulk%d T%4d S%d |' % (bulk, tile, stages)
+            for kind in kinds:
+                med, best = time_kind(kind)
+                gbs = bytes_per_elem[kind] * n / med / 1e3
+                row[kind] = dict(us=med, best_us=best, gbs=gbs, frac=gbs / peak)
+                msg += ' %s %6.1fus %4.0f (%.2f)' % (kind, med, gbs, gbs / peak)
+            print(msg, flush=True)
+            results.append(row)
+        grid = []
     print('workload %s n_elems %d buf %s peak %.1f GB/s' % (args.workload, n, args.buf, peak))
     for threads, unroll, ctas, persistent in grid:
         lib.gp_set_tuning(b'threads', threads)
