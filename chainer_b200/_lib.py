@@ -70,9 +70,9 @@ PROTOTYPES = {
     'gp_table_destroy': (c_int, [c_void_p]),
     'gp_table_upload': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, _P(c_void_p)]),
     'gp_pack': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
-                        c_double, c_void_p]),
+                        c_double, c_int, c_void_p]),
     'gp_unpack_scale': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
-                                c_double, c_void_p]),
+                                c_double, c_int, c_void_p]),
     'gp_unpack_momentum_sgd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
                                        c_int64, c_double, c_double, c_double, c_int, c_int, c_void_p]),
     'gp_unpack_adam': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,

@@ -280,7 +280,7 @@ def _batched_pack_params(params_data, buffer, dtype, stream=None, scale=1.0,
         elem_end = params_data.n_elems
     _lib.get().gp_pack(buffer.ptr(), _dev.dtype_id(dtype), params_data.d_csum,
                        params_data.d_segs, params_data.n_params, elem_begin, elem_end,
-                       float(scale), _dev.stream_ptr(stream))
+                       float(scale), params_data.layout_hint(dtype), _dev.stream_ptr(stream))
 
 
 def _batched_unpack_params(params_data, buffer, dtype, stream=None, scale=1.0,
@@ -291,7 +291,8 @@ def _batched_unpack_params(params_data, buffer, dtype, stream=None, scale=1.0,
         elem_end = params_data.n_elems
     _lib.get().gp_unpack_scale(buffer.ptr(), _dev.dtype_id(dtype), params_data.d_csum,
                                params_data.d_segs, params_data.n_params, elem_begin, elem_end,
-                               float(scale), _dev.stream_ptr(stream))
+                               float(scale), params_data.layout_hint(dtype),
+                               _dev.stream_ptr(stream))
 
 
 def pack_params(params, attr_name, buffer, transfer_dtype, zero_fill, stream=None):

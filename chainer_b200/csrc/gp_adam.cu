@@ -40,6 +40,7 @@ template <> struct AdamT<double> { using type = double; };
 template <bool AMS>
 struct AdamOp {
   static constexpr int kMaxUnroll = 2;
+  static constexpr int kMaxUnrollPipe = 2;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
   double alpha_t, omb1, omb2, eps, eta, wd, lower, upper;
@@ -81,35 +82,41 @@ struct AdamOp {
     v = v_;
   }
 
-  template <class B, class P, int U, int SM>
-  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
-                                      const bool (&act)[U]) const {
-    using CB = typename Carrier<B>::type;
-    using T = typename AdamT<P>::type;  // == Carrier<P>::type
-    constexpr bool ams = AMS;
+  template <class B, class P, int U> struct Regs {
     Raw4<B> rb[U];
-    Raw4<P> rp[U], rm[U], rv[U], rh[U];
+    Raw4<P> rp[U], rm[U], rv[U], rh[AMS ? U : 1];
+  };
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                       const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (act[u]) {
-        rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
-        rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
-        rm[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
-        rv[u] = ld4(mptr<P>(seg[u]->ptr[3]) + e[u]);
-        if constexpr (ams) rh[u] = ld4(mptr<P>(seg[u]->ptr[4]) + e[u]);
+        r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+        r.rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
+        r.rm[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
+        r.rv[u] = ld4(mptr<P>(seg[u]->ptr[3]) + e[u]);
+        if constexpr (AMS) r.rh[u] = ld4(mptr<P>(seg[u]->ptr[4]) + e[u]);
       }
     }
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                         const bool (&act)[U], const Regs<B, P, U>& r) const {
+    using CB = typename Carrier<B>::type;
+    using T = typename AdamT<P>::type;  // == Carrier<P>::type
     const Consts<T> c = consts<T>();
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       CB xb[4];
       T g[4], p[4], m[4], v[4], vh[4];
-      unpack4(rb[u], xb);
-      unpack4(rp[u], p);
-      unpack4(rm[u], m);
-      unpack4(rv[u], v);
-      if constexpr (ams) unpack4(rh[u], vh);
+      unpack4(r.rb[u], xb);
+      unpack4(r.rp[u], p);
+      unpack4(r.rm[u], m);
+      unpack4(r.rv[u], v);
+      if constexpr (AMS) unpack4(r.rh[u], vh);
       else { vh[0] = vh[1] = vh[2] = vh[3] = (T)0; }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -119,9 +126,16 @@ struct AdamOp {
       st4(mptr<P>(seg[u]->ptr[1]) + e[u], pack4<P, T>(p));
       st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, T>(m));
       st4(mptr<P>(seg[u]->ptr[3]) + e[u], pack4<P, T>(v));
-      if constexpr (ams) st4(mptr<P>(seg[u]->ptr[4]) + e[u], pack4<P, T>(vh));
+      if constexpr (AMS) st4(mptr<P>(seg[u]->ptr[4]) + e[u], pack4<P, T>(vh));
       if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, T>(g));
     }
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    Regs<B, P, U> r;
+    load<B, P, U>(seg, e, act, r);
+    finish<B, P, U, SM>(seg, e, act, r);
   }
 
   // TMA path: one tile, in place in shared memory (gp_bulk.cuh).
@@ -239,7 +253,7 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
       if (r <= 0) return r;
     }
     return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                           "gp_unpack_adam");
+                           "gp_unpack_adam", layout_hint == GP_F32);
   }
   AdamOp<false> op;
   op.buffer = buffer;
@@ -259,5 +273,5 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
     if (r <= 0) return r;
   }
   return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                         "gp_unpack_adam");
+                         "gp_unpack_adam", layout_hint == GP_F32);
 }

@@ -81,6 +81,9 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -112,12 +115,14 @@ struct BulkArgs {
   int n_arrays;
   ArrayDesc arr[kMaxArrays];
   uint32_t load_bytes_per_elem;
+  int chunk_bytes;  // bytes per bulk copy (multiple of 16)
+  int debug;  // experiments only: 1 = skip the bulk stores, 2 = skip the arithmetic
 };
 
 // Op interface:  template <class B, class P, int SM> static void tile(const Op&, char* stage,
 //                const BulkArgs&, int n_vec4)   -- consumers, in place in shared memory.
 template <class Op, class B, class P, int SM>
-__global__ void __launch_bounds__(kThreads, 1) bulk_kernel(const BulkArgs a, const Op op) {
+__global__ void __launch_bounds__(kThreads, 2) bulk_kernel(const BulkArgs a, const Op op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [csum int64[n+1]] [full[S]] [done[S]] [stages...]
   const int n = a.n_segs;
@@ -161,7 +166,11 @@ __global__ void __launch_bounds__(kThreads, 1) bulk_kernel(const BulkArgs a, con
       jf = gpw::seg_seek(s_csum, n, jf, t0);
       if (is_load && lane == 0) mbar_expect_tx(full + (k % S), (uint32_t)(t1 - t0) * a.load_bytes_per_elem);
       __syncwarp();
-      for (int j = jf + lane; j < n && s_csum[j] < t1; j += 32) {
+      // Work items = (piece, array, chunk); the 32 lanes take them round-robin.
+      // Chunking matters: one bulk copy is serviced with limited parallelism, so
+      // many concurrent copies of a few KB move more bytes than few large ones.
+      int item = 0;
+      for (int j = jf; j < n && s_csum[j] < t1; ++j) {
         const int64_t p0 = s_csum[j] > t0 ? s_csum[j] : t0;
         const int64_t p1 = s_csum[j + 1] < t1 ? s_csum[j + 1] : t1;
         if (p1 <= p0) continue;
@@ -174,12 +183,17 @@ __global__ void __launch_bounds__(kThreads, 1) bulk_kernel(const BulkArgs a, con
           if (q >= a.n_arrays) break;
           const ArrayDesc& d = a.arr[q];
           if (is_load ? !d.load : !d.store) continue;
-          unsigned char* sp = st + d.smem_off + (size_t)toff * d.itemsize;
-          unsigned char* gp = d.ptr_index < 0
-                                  ? (unsigned char*)a.buffer + (g->buf_off + e0) * d.itemsize
-                                  : (unsigned char*)g->ptr[d.ptr_index] + e0 * d.itemsize;
-          if (is_load) bulk_load(sp, gp, cnt * d.itemsize, full + (k % S));
-          else bulk_store(gp, sp, cnt * d.itemsize);
+          const uint32_t che = (uint32_t)a.chunk_bytes / (uint32_t)d.itemsize;  // elements per chunk
+          for (uint32_t c0 = 0; c0 < cnt; c0 += che, ++item) {
+            if ((item & 31) != lane) continue;
+            const uint32_t c1 = c0 + che < cnt ? c0 + che : cnt;
+            unsigned char* sp = st + d.smem_off + (size_t)(toff + c0) * d.itemsize;
+            unsigned char* gp = d.ptr_index < 0
+                                    ? (unsigned char*)a.buffer + (g->buf_off + e0 + c0) * d.itemsize
+                                    : (unsigned char*)g->ptr[d.ptr_index] + (e0 + c0) * d.itemsize;
+            if (is_load) bulk_load(sp, gp, (c1 - c0) * d.itemsize, full + (k % S));
+            else bulk_store(gp, sp, (c1 - c0) * d.itemsize);
+          }
         }
       }
     };
@@ -189,14 +203,18 @@ __global__ void __launch_bounds__(kThreads, 1) bulk_kernel(const BulkArgs a, con
     for (int j = 0; j < K; ++j) {
       if (lane == 0) mbar_wait(done + (j % S), (uint32_t)((j / S) & 1));
       __syncwarp();
-      issue(j, false, j_store);
+      if (!(a.debug & 1)) issue(j, false, j_store);
       bulk_commit();
-      if (j + S < K) {
-        bulk_wait_read0();  // the stage's shared memory has been read by the store engine
+      // Refill the stage of the PREVIOUS tile: its bulk store has had one whole
+      // tile time to read shared memory, so this wait does not stall the
+      // load-issuing chain (waiting on the store just issued costs ~1.4 us/tile).
+      if (j >= 1 && (j - 1) + S < K) {
+        bulk_wait_read1();
         __syncwarp();
-        issue(j + S, true, j_first);
+        issue(j - 1 + S, true, j_first);
       }
     }
+    if (K >= 1 && (K - 1) + S < K) { /* unreachable: the last tile never triggers a refill */ }
     bulk_wait0();  // all writes globally performed before the kernel ends
   } else {
     // ----------------------------------------------------------- consumers --
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) bulk_kernel(const BulkArgs a, con
       mbar_wait(full + s, (uint32_t)((k / S) & 1));
       const int64_t t0 = lo + (int64_t)k * T;
       const int n_el = (int)((hi - t0) < T ? (hi - t0) : T);
-      Op::template tile<B, P, SM>(op, stage0 + (size_t)s * a.stage_bytes, a, n_el >> 2);
+      if (!(a.debug & 2)) Op::template tile<B, P, SM>(op, stage0 + (size_t)s * a.stage_bytes, a, n_el >> 2);
       fence_proxy_async();  // make the in-place results visible to the bulk-store engine
       mbar_arrive(done + s);
     }
@@ -244,7 +262,7 @@ template <> __device__ __forceinline__ void sts4(__half* p, const Raw4<__half>& 
 
 // ------------------------------------------------------------- host side --
 struct BulkTuning {
-  int enable, tile, stages;
+  int enable, tile, stages, ctas, debug, chunk;
 };
 extern BulkTuning g_bulk_tuning;
 
@@ -267,7 +285,8 @@ int launch_bulk_t(BulkArgs a, const Op& op, cudaStream_t st, const char* what) {
   int stages = g_bulk_tuning.stages;
   const size_t fixed = ((((size_t)a.n_segs + 1) * 8 + 127) & ~(size_t)127) + 256;
   int stage_bytes = layout_stage(a, tile);
-  const size_t cap = 227 * 1024;
+  const int ctas = g_bulk_tuning.ctas >= 2 ? 2 : 1;
+  const size_t cap = ctas == 2 ? 113 * 1024 : 227 * 1024;
   while (stages > 2 && fixed + (size_t)stages * stage_bytes > cap) --stages;
   while (tile > 512 && fixed + (size_t)stages * stage_bytes > cap) {
     tile >>= 1;
@@ -275,18 +294,20 @@ int launch_bulk_t(BulkArgs a, const Op& op, cudaStream_t st, const char* what) {
   }
   if (fixed + (size_t)stages * stage_bytes > cap) return 1;  // does not fit: use the register path
   a.tile = tile;
+  a.debug = g_bulk_tuning.debug;
+  a.chunk_bytes = g_bulk_tuning.chunk < 256 ? 256 : (g_bulk_tuning.chunk & ~255);
   a.stages = stages;
   a.stage_bytes = stage_bytes;
   const size_t smem = fixed + (size_t)stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(bulk_kernel<Op, B, P, SM>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return gp_cuda_fail(e, "cudaFuncSetAttribute(bulk_kernel)");
     attr_set = true;
   }
   const int64_t total = a.end - a.begin;
-  int64_t grid = gp_sm_count_cached();
+  int64_t grid = (int64_t)gp_sm_count_cached() * ctas;
   const int64_t n_tiles = (total + tile - 1) / tile;
   if (grid > n_tiles) grid = n_tiles;
   int64_t per = (total + grid - 1) / grid;

@@ -22,6 +22,7 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // buffer[buf_off + k] = (B)(scale * ptr0[k])
 struct PackOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kMaxUnrollPipe = 4;  // two tiles live in registers
   void* buffer;
   ScaleArg s;
 
@@ -45,21 +46,33 @@ struct PackOp {
     }
   }
 
-  template <class B, class P, int U, int SM>
-  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
-                                      const bool (&act)[U]) const {
-    using CP = typename Carrier<P>::type;
-    Raw4<P> in[U];
+  template <class B, class P, int U> struct Regs { Raw4<P> in[U]; };
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                       const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (act[u]) in[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+      if (act[u]) r.in[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                         const bool (&act)[U], const Regs<B, P, U>& r) const {
+    using CP = typename Carrier<P>::type;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       CP x[4];
-      unpack4(in[u], x);
+      unpack4(r.in[u], x);
       st4(reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u], convert<B, SM, CP>(x));
     }
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    Regs<B, P, U> r;
+    load<B, P, U>(seg, e, act, r);
+    finish<B, P, U, SM>(seg, e, act, r);
   }
 
   template <class B, class P, int SM>
@@ -86,31 +99,45 @@ struct PackOp {
 // ptr0[k] = (P)( (B)(scale * buffer[buf_off + k]) )
 struct UnpackOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kMaxUnrollPipe = 4;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
 
-  template <class B, class P, int U, int SM>
-  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
-                                      const bool (&act)[U]) const {
-    using CB = typename Carrier<B>::type;
-    using CP = typename Carrier<P>::type;
-    Raw4<B> in[U];
+  template <class B, class P, int U> struct Regs { Raw4<B> in[U]; };
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                       const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (act[u]) in[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+      if (act[u]) r.in[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                         const bool (&act)[U], const Regs<B, P, U>& r) const {
+    using CB = typename Carrier<B>::type;
+    using CP = typename Carrier<P>::type;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       CB x[4];
       CP g[4];
-      unpack4(in[u], x);
+      unpack4(r.in[u], x);
 #pragma unroll
       for (int i = 0; i < 4; ++i) g[i] = gpw::mean_grad_value<B, P, SM>(x[i], s);
       st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
     }
   }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    Regs<B, P, U> r;
+    load<B, P, U>(seg, e, act, r);
+    finish<B, P, U, SM>(seg, e, act, r);
+  }
+
   template <class B, class P, int SM>
   __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
     const auto x = to_carrier(reinterpret_cast<const B*>(buffer)[g.buf_off + e]);
@@ -176,22 +203,22 @@ int flat_grid(int64_t n) {
 
 extern "C" int gp_pack(void* buffer, int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs,
                        int n_segs, int64_t elem_begin, int64_t elem_end, double scale,
-                       void* stream) {
+                       int layout_hint, void* stream) {
   PackOp op;
   op.buffer = buffer;
   op.s = make_scale(scale);
   return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                         "gp_pack");
+                         "gp_pack", layout_hint == GP_F32);
 }
 
 extern "C" int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
                                const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
-                               int64_t elem_end, double scale, void* stream) {
+                               int64_t elem_end, double scale, int layout_hint, void* stream) {
   UnpackOp op;
   op.buffer = buffer;
   op.s = make_scale(scale);
   return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                         "gp_unpack_scale");
+                         "gp_unpack_scale", layout_hint == GP_F32);
 }
 
 extern "C" int gp_scale(void* buffer, int dtype, int64_t n, double scale, void* stream) {

@@ -29,9 +29,9 @@ int gp_cuda_fail(cudaError_t e, const char* what) {
 
 // defaults: see DESIGN.md "tuning"
 GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 4, /*ctas_per_sm*/ 8, /*persistent*/ 1,
-                        /*bn_threads*/ 256};
+                        /*bn_threads*/ 256, /*pipeline*/ 1};
 
-gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 1, /*tile*/ 2048, /*stages*/ 4};
+gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 0, /*tile*/ 4096, /*stages*/ 4, /*ctas*/ 1, /*debug*/ 0, /*chunk*/ 2048};
 
 int gp_sm_count_cached() {
   static thread_local int cached_dev = -1;
@@ -60,9 +60,13 @@ int gp_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "ctas_per_sm")) g_gp_tuning.ctas_per_sm = value;
   else if (!strcmp(key, "persistent")) g_gp_tuning.persistent = value;
   else if (!strcmp(key, "bn_threads")) g_gp_tuning.bn_threads = value;
+  else if (!strcmp(key, "pipeline")) g_gp_tuning.pipeline = value;
   else if (!strcmp(key, "bulk")) gpb::g_bulk_tuning.enable = value;
   else if (!strcmp(key, "bulk_tile")) gpb::g_bulk_tuning.tile = value < 512 ? 512 : (value & ~511);
   else if (!strcmp(key, "bulk_stages")) gpb::g_bulk_tuning.stages = value < 2 ? 2 : value;
+  else if (!strcmp(key, "bulk_ctas")) gpb::g_bulk_tuning.ctas = value;
+  else if (!strcmp(key, "bulk_debug")) gpb::g_bulk_tuning.debug = value;
+  else if (!strcmp(key, "bulk_chunk")) gpb::g_bulk_tuning.chunk = value;
   else {
     gp_set_error("gp_set_tuning: unknown key '%s'", key);
     return GP_EINVAL;
@@ -76,9 +80,11 @@ int gp_get_tuning(const char* key, int* value) {
   else if (!strcmp(key, "ctas_per_sm")) *value = g_gp_tuning.ctas_per_sm;
   else if (!strcmp(key, "persistent")) *value = g_gp_tuning.persistent;
   else if (!strcmp(key, "bn_threads")) *value = g_gp_tuning.bn_threads;
+  else if (!strcmp(key, "pipeline")) *value = g_gp_tuning.pipeline;
   else if (!strcmp(key, "bulk")) *value = gpb::g_bulk_tuning.enable;
   else if (!strcmp(key, "bulk_tile")) *value = gpb::g_bulk_tuning.tile;
   else if (!strcmp(key, "bulk_stages")) *value = gpb::g_bulk_tuning.stages;
+  else if (!strcmp(key, "bulk_ctas")) *value = gpb::g_bulk_tuning.ctas;
   else {
     gp_set_error("gp_get_tuning: unknown key '%s'", key);
     return GP_EINVAL;

@@ -36,6 +36,7 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // ------------------------------------------------------------ MomentumSGD --
 struct SgdOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kMaxUnrollPipe = 2;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
   double lr, momentum;
@@ -56,30 +57,37 @@ struct SgdOp {
     p = A::add(p, v);
   }
 
-  template <class B, class P, int U, int SM>
-  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
-                                      const bool (&act)[U]) const {
-    using CB = typename Carrier<B>::type;
-    using CP = typename Carrier<P>::type;
+  template <class B, class P, int U> struct Regs {
     Raw4<B> rb[U];
     Raw4<P> rp[U], rv[U];
+  };
+
+  template <class B, class P, int U>
+  __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                       const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (act[u]) {
-        rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
-        rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
-        rv[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
+        r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+        r.rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
+        r.rv[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
       }
     }
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                         const bool (&act)[U], const Regs<B, P, U>& r) const {
+    using CB = typename Carrier<B>::type;
+    using CP = typename Carrier<P>::type;
     const CP lr_ = Arith<P>::cst(lr), mom_ = Arith<P>::cst(momentum);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       CB xb[4];
       CP g[4], p[4], v[4];
-      unpack4(rb[u], xb);
-      unpack4(rp[u], p);
-      unpack4(rv[u], v);
+      unpack4(r.rb[u], xb);
+      unpack4(r.rp[u], p);
+      unpack4(r.rv[u], v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         g[i] = gpw::mean_grad_value<B, P, SM>(xb[i], s);
@@ -89,6 +97,13 @@ struct SgdOp {
       st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, CP>(v));
       if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
     }
+  }
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    Regs<B, P, U> r;
+    load<B, P, U>(seg, e, act, r);
+    finish<B, P, U, SM>(seg, e, act, r);
   }
 
   // TMA path: one tile, in place in shared memory (gp_bulk.cuh)
@@ -186,6 +201,6 @@ extern "C" int gp_unpack_momentum_sgd(const void* buffer, int buf_dtype, const i
     if (r <= 0) return r;
   }
   return gpw::launch_buf(buf_dtype, d_csum, d_segs, n_segs, elem_begin, elem_end, op, stream,
-                         "gp_unpack_momentum_sgd");
+                         "gp_unpack_momentum_sgd", layout_hint == GP_F32);
 }
 

@@ -60,7 +60,7 @@ __device__ __forceinline__ int seg_seek(const int64_t* cs, int n, int j, int64_t
 //   template <class B, class P, int U, int SM> void vec(seg[U], e[U], act[U]) const
 //   template <class B, int SM> void scalar(const gp_seg_t&, int64_t e) const
 // B = buffer element type (per launch), P = parameter element type (per tile).
-template <class Op, class B, int U, int SM>
+template <class Op, class B, int U, int SM, int PT>
 __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, const Op op) {
   extern __shared__ int64_t s_csum[];
   const int n = a.n_segs;
@@ -122,10 +122,15 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
     ok = __all_sync(0xffffffffu, ok && my_key != GP_F64);
 
     if (ok) {
-      switch (my_key) {
-        case GP_F32: op.template vec<B, float, U, SM>(sg, e, act); break;
-        case GP_F16: op.template vec<B, __half, U, SM>(sg, e, act); break;
-        default: break;
+      if constexpr (PT == GP_F32) {
+        // the caller promised float32 everywhere: no dtype dispatch in the kernel
+        op.template vec<B, float, U, SM>(sg, e, act);
+      } else {
+        switch (my_key) {
+          case GP_F32: op.template vec<B, float, U, SM>(sg, e, act); break;
+          case GP_F16: op.template vec<B, __half, U, SM>(sg, e, act); break;
+          default: break;
+        }
       }
     } else {
       int js = j;
@@ -134,22 +139,131 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
         const int64_t flat = base + (int64_t)k * 32 + lane;
         if (flat < hi) {
           js = seg_seek(cs, n, js, flat);
-          op.template scalar<B, SM>(a.segs[js], flat - cs[js]);
+          if constexpr (PT == GP_F32) op.template one<B, float, SM>(a.segs[js], flat - cs[js]);
+          else op.template scalar<B, SM>(a.segs[js], flat - cs[js]);
         }
       }
     }
   }
 }
 
+// ------------------------------------------------------------------------
+// Software-pipelined variant for parameter lists that are float32 throughout
+// (layout promise of the caller, PT == GP_F32 above).  The register-path
+// walker alternates "issue loads -> wait -> arithmetic -> stores" per warp, so
+// the memory latency of a tile and the arithmetic of the previous one do not
+// overlap unless other warps happen to be out of phase.  Here every warp keeps
+// TWO tiles in registers: the loads of tile i+1 are issued before the
+// arithmetic and stores of tile i.  An Op supplies, besides vec/one:
+//   template <class B, class P, int U> struct Regs
+//   load<B, P, U>(seg, e, act, Regs&)  and  finish<B, P, U, SM>(seg, e, act, const Regs&)
+template <int U>
+struct TileCtx {
+  const gp_seg_t* sg[U];
+  int64_t e[U];
+  bool act[U];
+  bool ok;
+  int64_t base;
+  int j;
+};
+
+template <class Op, class B, int U, int SM>
+__global__ void __launch_bounds__(kMaxThreads) walk_pipe_kernel(const WalkArgs a, const Op op) {
+  extern __shared__ int64_t s_csum[];
+  const int n = a.n_segs;
+  const int64_t lo = a.begin + (int64_t)blockIdx.x * a.per_cta;
+  const int64_t hi = (lo + a.per_cta < a.end) ? lo + a.per_cta : a.end;
+  if (lo >= hi) return;
+
+  const int64_t* cs = a.csum;
+  if (a.use_smem) {
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_csum[i] = a.csum[i];
+    __syncthreads();
+    cs = s_csum;
+  }
+
+  constexpr int WT = 32 * U * 4;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t stride = (int64_t)(blockDim.x >> 5) * WT;
+  const int64_t base0 = lo + (int64_t)warp * WT;
+  if (base0 >= hi) return;
+
+  using R = typename Op::template Regs<B, float, U>;
+
+  auto resolve = [&](int64_t base, int j_hint, TileCtx<U>& c) {
+    c.base = base;
+    c.j = seg_seek(cs, n, j_hint, base);
+    bool ok = true;
+    int jj = c.j;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t flat0 = base + (int64_t)(u * 32 + lane) * 4;
+      c.act[u] = flat0 < hi;
+      if (c.act[u]) {
+        jj = seg_seek(cs, n, jj, flat0);
+        ok = ok && (flat0 + 4 <= hi) && (flat0 + 4 <= cs[jj + 1]);
+      }
+      c.sg[u] = a.segs + jj;
+      c.e[u] = flat0 - cs[jj];
+      if (c.act[u]) ok = ok && (c.sg[u]->flags & GP_SEG_VEC_OK);
+    }
+    c.ok = __all_sync(0xffffffffu, ok);
+  };
+  auto scalar_tile = [&](const TileCtx<U>& c) {
+    int js = c.j;
+#pragma unroll 1
+    for (int k = 0; k < U * 4; ++k) {
+      const int64_t flat = c.base + (int64_t)k * 32 + lane;
+      if (flat < hi) {
+        js = seg_seek(cs, n, js, flat);
+        op.template one<B, float, SM>(a.segs[js], flat - cs[js]);
+      }
+    }
+  };
+
+  TileCtx<U> c0, c1;
+  R r0, r1;
+  resolve(base0, seg_find(cs, n, base0), c0);
+  if (c0.ok) op.template load<B, float, U>(c0.sg, c0.e, c0.act, r0);
+  while (true) {
+    const int64_t b1 = c0.base + stride;
+    const bool has1 = b1 < hi;
+    if (has1) {
+      resolve(b1, c0.j, c1);
+      if (c1.ok) op.template load<B, float, U>(c1.sg, c1.e, c1.act, r1);
+    }
+    if (c0.ok) op.template finish<B, float, U, SM>(c0.sg, c0.e, c0.act, r0);
+    else scalar_tile(c0);
+    if (!has1) break;
+    const int64_t b0 = c1.base + stride;
+    const bool has0 = b0 < hi;
+    if (has0) {
+      resolve(b0, c1.j, c0);
+      if (c0.ok) op.template load<B, float, U>(c0.sg, c0.e, c0.act, r0);
+    }
+    if (c1.ok) op.template finish<B, float, U, SM>(c1.sg, c1.e, c1.act, r1);
+    else scalar_tile(c1);
+    if (!has0) break;
+  }
+}
+
 // resident CTAs per SM of one instantiation (cached: the occupancy query is a
 // host-side calculation but not free)
-template <class Op, class B, int U, int SM>
+constexpr int kPipe = 1007;  // PT value selecting walk_pipe_kernel (float32 lists, pipelined)
+
+template <class Op, class B, int U, int SM, int PT>
 int resident_ctas(int threads, size_t smem) {
   static int c_threads = -1, c_occ = 1;
   static size_t c_smem = 0;
   if (threads != c_threads || smem != c_smem) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U, SM>, threads, smem) !=
+    cudaError_t qe;
+    if constexpr (PT == kPipe)
+      qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_pipe_kernel<Op, B, U, SM>, threads, smem);
+    else
+      qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U, SM, PT>, threads, smem);
+    if (qe !=
             cudaSuccess || occ < 1) {
       (void)cudaGetLastError();
       occ = 1;
@@ -161,7 +275,7 @@ int resident_ctas(int threads, size_t smem) {
   return c_occ;
 }
 
-template <class Op, class B, int U, int SM>
+template <class Op, class B, int U, int SM, int PT>
 int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st, const char* what) {
   const GpTuning& t = g_gp_tuning;
   const int64_t total = a.end - a.begin;
@@ -170,7 +284,7 @@ int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st
   if (t.persistent) {
     // every CTA must be resident at once, otherwise the equal slices would run
     // in waves: cap the grid by the real occupancy of this instantiation.
-    int per_sm = resident_ctas<Op, B, U, SM>(threads, smem);
+    int per_sm = resident_ctas<Op, B, U, SM, PT>(threads, smem);
     if (t.ctas_per_sm > 0 && t.ctas_per_sm < per_sm) per_sm = t.ctas_per_sm;
     const int64_t max_grid = (int64_t)gp_sm_count_cached() * per_sm;
     grid = (total + cta_tile - 1) / cta_tile;
@@ -187,14 +301,15 @@ int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st
     gp_set_error("%s: grid too large", what);
     return GP_EINVAL;
   }
-  walk_kernel<Op, B, U, SM><<<(unsigned)grid, threads, smem, st>>>(a, op);
+  if constexpr (PT == kPipe) walk_pipe_kernel<Op, B, U, SM><<<(unsigned)grid, threads, smem, st>>>(a, op);
+  else walk_kernel<Op, B, U, SM, PT><<<(unsigned)grid, threads, smem, st>>>(a, op);
   return gp_cuda_fail(cudaGetLastError(), what);
 }
 
 // Choose the grid and launch.  `what` only labels error messages.
 template <class Op, class B>
 int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t begin, int64_t end,
-           const Op& op, void* stream, const char* what) {
+           const Op& op, void* stream, const char* what, bool f32 = false) {
   if (n_segs <= 0 || end <= begin) return 0;
   if (begin < 0 || (begin & 3)) {
     gp_set_error("%s: elem_begin (%lld) must be a non-negative multiple of 4", what,
@@ -208,7 +323,8 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
   threads &= ~31;
   int U = t.unroll >= 4 ? 4 : 2;
   if (sizeof(B) == 8 && U > 2) U = 2;
-  if (U > Op::kMaxUnroll) U = Op::kMaxUnroll;
+  if (U > Op::kMaxUnroll && !f32) U = Op::kMaxUnroll;  // the float32-only variants are leaner
+  if (f32 && g_gp_tuning.pipeline && U > Op::kMaxUnrollPipe) U = Op::kMaxUnrollPipe;
 
   WalkArgs a;
   a.csum = d_csum;
@@ -222,11 +338,16 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
 
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = op.s.mode;
+  const bool pipe = g_gp_tuning.pipeline != 0;
 #define GP_LAUNCH(UU)                                                              \
   switch (mode) {                                                                  \
-    case 0: return launch_u<Op, B, UU, 0>(a, op, threads, smem, st, what);         \
-    case 1: return launch_u<Op, B, UU, 1>(a, op, threads, smem, st, what);         \
-    default: return launch_u<Op, B, UU, 2>(a, op, threads, smem, st, what);        \
+    case 0: return !f32 ? launch_u<Op, B, UU, 0, 0>(a, op, threads, smem, st, what)               \
+                 : pipe ? launch_u<Op, B, UU, 0, kPipe>(a, op, threads, smem, st, what)           \
+                        : launch_u<Op, B, UU, 0, GP_F32>(a, op, threads, smem, st, what);         \
+    case 1: return !f32 ? launch_u<Op, B, UU, 1, 0>(a, op, threads, smem, st, what)               \
+                 : pipe ? launch_u<Op, B, UU, 1, kPipe>(a, op, threads, smem, st, what)           \
+                        : launch_u<Op, B, UU, 1, GP_F32>(a, op, threads, smem, st, what);         \
+    default: return launch_u<Op, B, UU, 2, 0>(a, op, threads, smem, st, what);             \
   }
   if (U >= 4) { GP_LAUNCH(4) }
   GP_LAUNCH(2)
@@ -234,13 +355,15 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
 }
 
 // dispatch on the runtime buffer dtype
+// f32: the caller promises that every segment's arrays are float32 (layout_hint)
 template <class Op>
 int launch_buf(int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs,
-               int64_t begin, int64_t end, const Op& op, void* stream, const char* what) {
+               int64_t begin, int64_t end, const Op& op, void* stream, const char* what,
+               bool f32 = false) {
   switch (buf_dtype) {
-    case GP_F32: return launch<Op, float>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
-    case GP_F16: return launch<Op, __half>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
-    case GP_BF16: return launch<Op, __nv_bfloat16>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
+    case GP_F32: return launch<Op, float>(d_csum, d_segs, n_segs, begin, end, op, stream, what, f32);
+    case GP_F16: return launch<Op, __half>(d_csum, d_segs, n_segs, begin, end, op, stream, what, f32);
+    case GP_BF16: return launch<Op, __nv_bfloat16>(d_csum, d_segs, n_segs, begin, end, op, stream, what, f32);
     case GP_F64: return launch<Op, double>(d_csum, d_segs, n_segs, begin, end, op, stream, what);
     default:
       gp_set_error("%s: unsupported buffer dtype id %d", what, buf_dtype);

@@ -133,7 +133,8 @@ int gp_table_upload(void* table, const void* host_src, size_t nbytes, void* stre
  * for everything.
  */
 int gp_pack(void* buffer, int buf_dtype, const int64_t* d_csum, const gp_seg_t* d_segs,
-            int n_segs, int64_t elem_begin, int64_t elem_end, double scale, void* stream);
+            int n_segs, int64_t elem_begin, int64_t elem_end, double scale, int layout_hint,
+            void* stream);
 
 /*
  * gp_unpack_scale: ptr0[k] = (dtype0)( (buf_dtype)(scale * buffer[buf_off + k]) ).
@@ -145,15 +146,16 @@ int gp_pack(void* buffer, int buf_dtype, const int64_t* d_csum, const gp_seg_t* 
  */
 int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
                     const gp_seg_t* d_segs, int n_segs, int64_t elem_begin, int64_t elem_end,
-                    double scale, void* stream);
+                    double scale, int layout_hint, void* stream);
 
 /*
- * layout_hint (fused update kernels): 0 = no promise (register-path kernel);
- * GP_F32 = the caller guarantees that every segment has dtype0 == dtype1 ==
- * float32, every pointer is 16-byte aligned and every csum / buf_off value is a
- * multiple of 8 elements (4 suffices with a 4-byte buffer dtype).  The library
- * then uses the TMA-staged kernel (gp_bulk.cuh): 1-D bulk copies into a ring of
- * shared-memory stages, arithmetic from shared memory, bulk stores back.
+ * layout_hint (all four stream kernels): 0 = no promise; GP_F32 = the caller
+ * guarantees that every segment has dtype0 == dtype1 == float32, every pointer
+ * is 16-byte aligned and every csum / buf_off value is a multiple of 8 elements
+ * (4 suffices with a 4-byte buffer dtype).  The library then runs its
+ * float32-only kernels: the software-pipelined walker (two tiles in registers
+ * per warp, no dtype dispatch) or, when enabled by gp_set_tuning("bulk", 1),
+ * the TMA-staged kernel of gp_bulk.cuh.  Results are identical either way.
  *
  * gp_unpack_momentum_sgd: fused unpack + descale + MomentumSGD update.
  *   g = (dtype0)((buf_dtype)(scale * buffer[buf_off + k]))

@@ -187,7 +187,7 @@ class FakeLib(object):
             if lo < hi:
                 yield j, lo - int(csum[j]), hi - int(csum[j])
 
-    def gp_pack(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, stream):
+    def gp_pack(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, layout_hint, stream):
         self.calls.append(('gp_pack', (buf_dtype, n, begin, end, scale)))
         assert begin % 4 == 0
         csum, segs = self._tables_of(d_csum, d_segs, n)
@@ -204,7 +204,8 @@ class FakeLib(object):
         raw = _buf_read(int(buffer) + (off + e0) * isz, e1 - e0, buf_dtype)
         return og.scale_buffer(np.array(raw), _ID2DT[buf_dtype], scale).astype(gdt)
 
-    def gp_unpack_scale(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, stream):
+    def gp_unpack_scale(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, layout_hint,
+                        stream):
         self.calls.append(('gp_unpack_scale', (buf_dtype, n, begin, end, scale)))
         csum, segs = self._tables_of(d_csum, d_segs, n)
         for j, e0, e1 in self._pieces(csum, n, begin, end):

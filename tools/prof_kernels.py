@@ -55,10 +55,10 @@ def main():
         for _ in range(args.reps):
             flush.zero_()        # evict L2 between launches (a vectorized fill, not walk_kernel)
             if kind == 'pack':
-                lib.gp_pack(buf.data_ptr(), bid, pd_sgd.d_csum, pd_sgd.d_segs, len(sizes), 0, n, 1.0, 0)
+                lib.gp_pack(buf.data_ptr(), bid, pd_sgd.d_csum, pd_sgd.d_segs, len(sizes), 0, n, 1.0, hint, 0)
             elif kind == 'unpack':
                 lib.gp_unpack_scale(buf.data_ptr(), bid, pd_sgd.d_csum, pd_sgd.d_segs, len(sizes), 0, n,
-                                    0.125, 0)
+                                    0.125, hint, 0)
             elif kind in ('sgd', 'sgd_wg'):
                 lib.gp_unpack_momentum_sgd(buf.data_ptr(), bid, pd_sgd.d_csum, pd_sgd.d_segs,
                                            len(sizes), 0, n, 0.125, 0.01, 0.9,

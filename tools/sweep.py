@@ -43,6 +43,7 @@ def main():
     ap.add_argument('--out', default='gpurun_out/sweep.json')
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--bulk-sweep', action='store_true', help='sweep the TMA-staged kernels (tile, stages)')
+    ap.add_argument('--bulk-debug', action='store_true', help='experiment: skip stores / arithmetic')
     args = ap.parse_args()
     lib = _lib.get()
     plist = workloads.WORKLOADS[args.workload]()
@@ -72,10 +73,10 @@ def main():
         hint = st['pd_sgd'].layout_hint(bnp)
         if kind == 'pack':
             lib.gp_pack(st['buf'].data_ptr(), bid, st['pd_sgd'].d_csum, st['pd_sgd'].d_segs,
-                        len(sizes), 0, n, 1.0, 0)
+                        len(sizes), 0, n, 1.0, hint, 0)
         elif kind == 'unpack':
             lib.gp_unpack_scale(st['buf'].data_ptr(), bid, st['pd_sgd'].d_csum, st['pd_sgd'].d_segs,
-                                len(sizes), 0, n, 0.125, 0)
+                                len(sizes), 0, n, 0.125, hint, 0)
         elif kind in ('sgd', 'sgd_wg'):
             lib.gp_unpack_momentum_sgd(st['buf'].data_ptr(), bid, st['pd_sgd'].d_csum,
                                        st['pd_sgd'].d_segs, len(sizes), 0, n, 0.125, 0.01, 0.9,
@@ -108,20 +109,54 @@ def main():
         return ts[len(ts) // 2], ts[0]
 
     if args.quick:
-        grid = [(256, 4, 8, 1)]
+        lib.gp_set_tuning(b'bulk', 0)
+        grid = []
+        for pipe in (1, 0):
+            lib.gp_set_tuning(b'pipeline', pipe)
+            for threads, unroll, ctas in [(256, 4, 8), (256, 2, 8), (512, 2, 8), (128, 4, 8), (128, 2, 8)]:
+                lib.gp_set_tuning(b'threads', threads)
+                lib.gp_set_tuning(b'unroll', unroll)
+                lib.gp_set_tuning(b'ctas_per_sm', ctas)
+                msg = 'pipe%d t%3d u%d |' % (pipe, threads, unroll)
+                for kind in ['pack', 'unpack', 'sgd', 'sgd_wg', 'adam', 'adam_wg']:
+                    med, best = time_kind(kind)
+                    gbs = bytes_per_elem[kind] * n / med / 1e3
+                    msg += ' %s %6.1fus %4.0f (%.2f)' % (kind, med, gbs, gbs / peak)
+                print(msg, flush=True)
     else:
         grid = list(itertools.product([128, 256, 512], [1, 2, 4], [2, 4, 8, 16], [1])) + \
             list(itertools.product([128, 256, 512], [1, 2, 4], [0], [0]))
     results = []
     kinds = ['pack', 'unpack', 'sgd', 'sgd_wg', 'adam', 'adam_wg']
+    if args.bulk_debug:
+        kinds = ['sgd', 'adam']
+        lib.gp_set_tuning(b'bulk', 1)
+        for dbg, chunk in [(3, 8192), (3, 4096), (3, 2048), (3, 1024), (3, 512), (0, 4096), (0, 2048),
+                           (0, 1024), (0, 512)]:
+            for tile, stages, ctas in [(2048, 4, 1), (4096, 4, 1), (2048, 3, 2), (1024, 6, 2)]:
+                lib.gp_set_tuning(b'bulk_chunk', chunk)
+                lib.gp_set_tuning(b'bulk_tile', tile)
+                lib.gp_set_tuning(b'bulk_stages', stages)
+                lib.gp_set_tuning(b'bulk_ctas', ctas)
+                lib.gp_set_tuning(b'bulk_debug', dbg)
+                msg = 'debug%d chunk%4d T%4d S%d C%d |' % (dbg, chunk, tile, stages, ctas)
+                for kind in kinds:
+                    med, best = time_kind(kind)
+                    msg += ' %s %6.1fus' % (kind, med)
+                print(msg, flush=True)
+        lib.gp_set_tuning(b'bulk_debug', 0)
+        return
     if args.bulk_sweep:
         kinds = ['sgd', 'sgd_wg', 'adam', 'adam_wg']
-        for bulk, tile, stages in [(0, 2048, 4)] + [(1, t, s) for t in (1024, 2048, 4096) for s in (2, 3, 4, 6)]:
+        combos = [(0, 2048, 4, 1)] + [(1, t, s, c) for c in (1, 2) for t in (1024, 2048, 4096)
+                                      for s in (3, 4, 6, 8)]
+        for bulk, tile, stages, ctas in combos:
             lib.gp_set_tuning(b'bulk', bulk)
             lib.gp_set_tuning(b'bulk_tile', tile)
             lib.gp_set_tuning(b'bulk_stages', stages)
-            row = dict(bulk=bulk, tile=tile, stages=stages)
-            msg = 'bulk%d T%4d S%d |' % (bulk, tile, stages)
+            lib.gp_set_tuning(b'bulk_ctas', ctas)
+            row = dict(bulk=bulk, tile=tile, stages=stages, ctas=ctas)
+            msg = 'bulk%d T%4d S%d C%d |' % (bulk, tile, stages, ctas)
             for kind in kinds:
                 med, best = time_kind(kind)
                 gbs = bytes_per_elem[kind] * n / med / 1e3
