@@ -40,7 +40,6 @@ template <> struct AdamT<double> { using type = double; };
 template <bool AMS>
 struct AdamOp {
   static constexpr int kMaxUnroll = 2;
-  static constexpr int kMaxUnrollPipe = 2;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
   double alpha_t, omb1, omb2, eps, eta, wd, lower, upper;
@@ -85,6 +84,7 @@ struct AdamOp {
   template <class B, class P, int U> struct Regs {
     Raw4<B> rb[U];
     Raw4<P> rp[U], rm[U], rv[U], rh[AMS ? U : 1];
+    P *pp[U], *pm[U], *pv[U], *ph[AMS ? U : 1], *pg[U];  // resolved once, before any store
   };
 
   template <class B, class P, int U>
@@ -93,11 +93,16 @@ struct AdamOp {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (act[u]) {
+        r.pp[u] = mptr<P>(seg[u]->ptr[1]) + e[u];
+        r.pm[u] = mptr<P>(seg[u]->ptr[2]) + e[u];
+        r.pv[u] = mptr<P>(seg[u]->ptr[3]) + e[u];
+        r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
+        if constexpr (AMS) r.ph[u] = mptr<P>(seg[u]->ptr[4]) + e[u];
         r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
-        r.rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
-        r.rm[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
-        r.rv[u] = ld4(mptr<P>(seg[u]->ptr[3]) + e[u]);
-        if constexpr (AMS) r.rh[u] = ld4(mptr<P>(seg[u]->ptr[4]) + e[u]);
+        r.rp[u] = ld4(r.pp[u]);
+        r.rm[u] = ld4(r.pm[u]);
+        r.rv[u] = ld4(r.pv[u]);
+        if constexpr (AMS) r.rh[u] = ld4(r.ph[u]);
       }
     }
   }
@@ -123,11 +128,11 @@ struct AdamOp {
         g[i] = gpw::mean_grad_value<B, P, SM>(xb[i], s);
         math<P, T>(g[i], p[i], m[i], v[i], vh[i], c);
       }
-      st4(mptr<P>(seg[u]->ptr[1]) + e[u], pack4<P, T>(p));
-      st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, T>(m));
-      st4(mptr<P>(seg[u]->ptr[3]) + e[u], pack4<P, T>(v));
-      if constexpr (AMS) st4(mptr<P>(seg[u]->ptr[4]) + e[u], pack4<P, T>(vh));
-      if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, T>(g));
+      st4(r.pp[u], pack4<P, T>(p));
+      st4(r.pm[u], pack4<P, T>(m));
+      st4(r.pv[u], pack4<P, T>(v));
+      if constexpr (AMS) st4(r.ph[u], pack4<P, T>(vh));
+      if (write_grad) st4(r.pg[u], pack4<P, T>(g));
     }
   }
   template <class B, class P, int U, int SM>

@@ -22,7 +22,6 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // buffer[buf_off + k] = (B)(scale * ptr0[k])
 struct PackOp {
   static constexpr int kMaxUnroll = 4;
-  static constexpr int kMaxUnrollPipe = 4;  // two tiles live in registers
   void* buffer;
   ScaleArg s;
 
@@ -46,14 +45,17 @@ struct PackOp {
     }
   }
 
-  template <class B, class P, int U> struct Regs { Raw4<P> in[U]; };
+  template <class B, class P, int U> struct Regs { Raw4<P> in[U]; B* dst[U]; };
 
   template <class B, class P, int U>
   __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                        const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (act[u]) r.in[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+      if (act[u]) {
+        r.dst[u] = reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u];
+        r.in[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+      }
   }
   template <class B, class P, int U, int SM>
   __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
@@ -64,7 +66,7 @@ struct PackOp {
       if (!act[u]) continue;
       CP x[4];
       unpack4(r.in[u], x);
-      st4(reinterpret_cast<B*>(buffer) + seg[u]->buf_off + e[u], convert<B, SM, CP>(x));
+      st4(r.dst[u], convert<B, SM, CP>(x));
     }
   }
   template <class B, class P, int U, int SM>
@@ -99,20 +101,22 @@ struct PackOp {
 // ptr0[k] = (P)( (B)(scale * buffer[buf_off + k]) )
 struct UnpackOp {
   static constexpr int kMaxUnroll = 4;
-  static constexpr int kMaxUnrollPipe = 4;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype0; }
 
-  template <class B, class P, int U> struct Regs { Raw4<B> in[U]; };
+  template <class B, class P, int U> struct Regs { Raw4<B> in[U]; P* dst[U]; };
 
   template <class B, class P, int U>
   __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                        const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (act[u]) r.in[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+      if (act[u]) {
+        r.dst[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
+        r.in[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+      }
   }
   template <class B, class P, int U, int SM>
   __device__ __forceinline__ void finish(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
@@ -127,7 +131,7 @@ struct UnpackOp {
       unpack4(r.in[u], x);
 #pragma unroll
       for (int i = 0; i < 4; ++i) g[i] = gpw::mean_grad_value<B, P, SM>(x[i], s);
-      st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
+      st4(r.dst[u], pack4<P, CP>(g));
     }
   }
   template <class B, class P, int U, int SM>

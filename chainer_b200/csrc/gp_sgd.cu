@@ -36,7 +36,6 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // ------------------------------------------------------------ MomentumSGD --
 struct SgdOp {
   static constexpr int kMaxUnroll = 4;
-  static constexpr int kMaxUnrollPipe = 2;  // two tiles live in registers
   const void* buffer;
   ScaleArg s;
   double lr, momentum;
@@ -60,6 +59,7 @@ struct SgdOp {
   template <class B, class P, int U> struct Regs {
     Raw4<B> rb[U];
     Raw4<P> rp[U], rv[U];
+    P *pp[U], *pv[U], *pg[U];  // resolved once, before any store (no table re-reads)
   };
 
   template <class B, class P, int U>
@@ -68,9 +68,12 @@ struct SgdOp {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (act[u]) {
+        r.pp[u] = mptr<P>(seg[u]->ptr[1]) + e[u];
+        r.pv[u] = mptr<P>(seg[u]->ptr[2]) + e[u];
+        r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
         r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
-        r.rp[u] = ld4(mptr<P>(seg[u]->ptr[1]) + e[u]);
-        r.rv[u] = ld4(mptr<P>(seg[u]->ptr[2]) + e[u]);
+        r.rp[u] = ld4(r.pp[u]);
+        r.rv[u] = ld4(r.pv[u]);
       }
     }
   }
@@ -93,9 +96,9 @@ struct SgdOp {
         g[i] = gpw::mean_grad_value<B, P, SM>(xb[i], s);
         math<P>(g[i], p[i], v[i], lr_, mom_);
       }
-      st4(mptr<P>(seg[u]->ptr[1]) + e[u], pack4<P, CP>(p));
-      st4(mptr<P>(seg[u]->ptr[2]) + e[u], pack4<P, CP>(v));
-      if (write_grad) st4(mptr<P>(seg[u]->ptr[0]) + e[u], pack4<P, CP>(g));
+      st4(r.pp[u], pack4<P, CP>(p));
+      st4(r.pv[u], pack4<P, CP>(v));
+      if (write_grad) st4(r.pg[u], pack4<P, CP>(g));
     }
   }
   template <class B, class P, int U, int SM>

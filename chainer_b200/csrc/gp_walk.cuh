@@ -15,14 +15,15 @@
 //   * The cumulative-size table (int64[n+1]) is staged into shared memory once
 //     per CTA; a warp finds the parameter of its first element with one binary
 //     search in shared memory and afterwards only walks forward.
-//   * A warp tile is 32 lanes x U vectors x 4 elements.  If every vector of the
-//     tile lies inside a 4-aligned parameter and all of them have one dtype,
+//   * A warp tile is U rows of 32 lanes x 4 elements.  If every row of the tile
+//     lies inside a 4-aligned parameter and all rows have one dtype (resolved
+//     per ROW with warp-uniform lookups, not per lane),
 //     the tile runs in VECTOR mode: the loads of all U vectors of all arrays are
 //     issued first (8/16 B per lane, one warp instruction = 256/512 contiguous
 //     bytes), then the arithmetic, then the stores.  Otherwise (ragged sizes,
 //     mixed dtypes, the tail) the tile runs in SCALAR mode with a lane-coalesced
-//     element mapping.  Tiny parameters cost nothing extra: neighbouring lanes
-//     simply resolve to different table entries.
+//     element mapping, where neighbouring lanes simply resolve to different
+//     table entries (runs of tiny parameters).
 #pragma once
 #include "gp_common.cuh"
 
@@ -86,53 +87,45 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
   for (; base < hi; base += stride) {
     j = seg_seek(cs, n, j, base);
 
+    // Resolve the tile row by row (a row = 32 lanes x 4 elements = 128 flat
+    // elements).  Everything here is warp-uniform: one table lookup per ROW, not
+    // per lane.  A row is a vector row if it lies inside one 4-aligned
+    // parameter; the tile runs in vector mode if all its U rows are vector rows
+    // of one dtype (rows may belong to different parameters).
     const gp_seg_t* sg[U];
     int64_t e[U];
     bool act[U];
-    bool ok = true;
-    int my_key = 0;
-    int jj = j;
+    bool ok = base + WT <= hi;
+    int key0 = 0;
+    int jr = j;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t flat0 = base + (int64_t)(u * 32 + lane) * 4;
-      act[u] = flat0 < hi;
-      if (act[u]) {
-        jj = seg_seek(cs, n, jj, flat0);
-        ok = ok && (flat0 + 4 <= hi) && (flat0 + 4 <= cs[jj + 1]);
-      }
-      sg[u] = a.segs + jj;
-      e[u] = flat0 - cs[jj];
-    }
-    // lane 0 / u == 0 is always active (base < hi): its dtype is the tile's key
-    {
-      const int k0 = Op::key(*sg[0]);
-      const int key_ref = __shfl_sync(0xffffffffu, k0, 0);
-      my_key = key_ref;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (act[u]) {
-          const gp_seg_t& g = *sg[u];
-          ok = ok && (g.flags & GP_SEG_VEC_OK) && (Op::key(g) == key_ref);
-        }
+      const int64_t row = base + u * 128;
+      sg[u] = a.segs + jr;
+      e[u] = 0;
+      act[u] = true;
+      if (ok) {
+        jr = seg_seek(cs, n, jr, row);
+        const gp_seg_t* g = a.segs + jr;
+        const int k = Op::key(*g);
+        if (u == 0) key0 = k;
+        ok = (row + 128 <= cs[jr + 1]) && (g->flags & GP_SEG_VEC_OK) && k == key0 && k != GP_F64;
+        sg[u] = g;
+        e[u] = row - cs[jr] + (int64_t)lane * 4;
       }
     }
-    // float64 parameters (rare: tests, scientific models) take the scalar path;
-    // keeping their vector bodies out of the kernel keeps the register count of
-    // the float32 / float16 stream low.
-    ok = __all_sync(0xffffffffu, ok && my_key != GP_F64);
 
     if (ok) {
       if constexpr (PT == GP_F32) {
         // the caller promised float32 everywhere: no dtype dispatch in the kernel
         op.template vec<B, float, U, SM>(sg, e, act);
       } else {
-        switch (my_key) {
-          case GP_F32: op.template vec<B, float, U, SM>(sg, e, act); break;
-          case GP_F16: op.template vec<B, __half, U, SM>(sg, e, act); break;
-          default: break;
-        }
+        if (key0 == GP_F32) op.template vec<B, float, U, SM>(sg, e, act);
+        else op.template vec<B, __half, U, SM>(sg, e, act);
       }
     } else {
+      // ragged sizes, mixed dtypes, float64, tiny parameters, the tail:
+      // lane-coalesced scalar elements
       int js = j;
 #pragma unroll 1
       for (int k = 0; k < U * 4; ++k) {
@@ -147,123 +140,15 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
   }
 }
 
-// ------------------------------------------------------------------------
-// Software-pipelined variant for parameter lists that are float32 throughout
-// (layout promise of the caller, PT == GP_F32 above).  The register-path
-// walker alternates "issue loads -> wait -> arithmetic -> stores" per warp, so
-// the memory latency of a tile and the arithmetic of the previous one do not
-// overlap unless other warps happen to be out of phase.  Here every warp keeps
-// TWO tiles in registers: the loads of tile i+1 are issued before the
-// arithmetic and stores of tile i.  An Op supplies, besides vec/one:
-//   template <class B, class P, int U> struct Regs
-//   load<B, P, U>(seg, e, act, Regs&)  and  finish<B, P, U, SM>(seg, e, act, const Regs&)
-template <int U>
-struct TileCtx {
-  const gp_seg_t* sg[U];
-  int64_t e[U];
-  bool act[U];
-  bool ok;
-  int64_t base;
-  int j;
-};
-
-template <class Op, class B, int U, int SM>
-__global__ void __launch_bounds__(kMaxThreads) walk_pipe_kernel(const WalkArgs a, const Op op) {
-  extern __shared__ int64_t s_csum[];
-  const int n = a.n_segs;
-  const int64_t lo = a.begin + (int64_t)blockIdx.x * a.per_cta;
-  const int64_t hi = (lo + a.per_cta < a.end) ? lo + a.per_cta : a.end;
-  if (lo >= hi) return;
-
-  const int64_t* cs = a.csum;
-  if (a.use_smem) {
-    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_csum[i] = a.csum[i];
-    __syncthreads();
-    cs = s_csum;
-  }
-
-  constexpr int WT = 32 * U * 4;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int64_t stride = (int64_t)(blockDim.x >> 5) * WT;
-  const int64_t base0 = lo + (int64_t)warp * WT;
-  if (base0 >= hi) return;
-
-  using R = typename Op::template Regs<B, float, U>;
-
-  auto resolve = [&](int64_t base, int j_hint, TileCtx<U>& c) {
-    c.base = base;
-    c.j = seg_seek(cs, n, j_hint, base);
-    bool ok = true;
-    int jj = c.j;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t flat0 = base + (int64_t)(u * 32 + lane) * 4;
-      c.act[u] = flat0 < hi;
-      if (c.act[u]) {
-        jj = seg_seek(cs, n, jj, flat0);
-        ok = ok && (flat0 + 4 <= hi) && (flat0 + 4 <= cs[jj + 1]);
-      }
-      c.sg[u] = a.segs + jj;
-      c.e[u] = flat0 - cs[jj];
-      if (c.act[u]) ok = ok && (c.sg[u]->flags & GP_SEG_VEC_OK);
-    }
-    c.ok = __all_sync(0xffffffffu, ok);
-  };
-  auto scalar_tile = [&](const TileCtx<U>& c) {
-    int js = c.j;
-#pragma unroll 1
-    for (int k = 0; k < U * 4; ++k) {
-      const int64_t flat = c.base + (int64_t)k * 32 + lane;
-      if (flat < hi) {
-        js = seg_seek(cs, n, js, flat);
-        op.template one<B, float, SM>(a.segs[js], flat - cs[js]);
-      }
-    }
-  };
-
-  TileCtx<U> c0, c1;
-  R r0, r1;
-  resolve(base0, seg_find(cs, n, base0), c0);
-  if (c0.ok) op.template load<B, float, U>(c0.sg, c0.e, c0.act, r0);
-  while (true) {
-    const int64_t b1 = c0.base + stride;
-    const bool has1 = b1 < hi;
-    if (has1) {
-      resolve(b1, c0.j, c1);
-      if (c1.ok) op.template load<B, float, U>(c1.sg, c1.e, c1.act, r1);
-    }
-    if (c0.ok) op.template finish<B, float, U, SM>(c0.sg, c0.e, c0.act, r0);
-    else scalar_tile(c0);
-    if (!has1) break;
-    const int64_t b0 = c1.base + stride;
-    const bool has0 = b0 < hi;
-    if (has0) {
-      resolve(b0, c1.j, c0);
-      if (c0.ok) op.template load<B, float, U>(c0.sg, c0.e, c0.act, r0);
-    }
-    if (c1.ok) op.template finish<B, float, U, SM>(c1.sg, c1.e, c1.act, r1);
-    else scalar_tile(c1);
-    if (!has0) break;
-  }
-}
-
 // resident CTAs per SM of one instantiation (cached: the occupancy query is a
 // host-side calculation but not free)
-constexpr int kPipe = 1007;  // PT value selecting walk_pipe_kernel (float32 lists, pipelined)
-
 template <class Op, class B, int U, int SM, int PT>
 int resident_ctas(int threads, size_t smem) {
   static int c_threads = -1, c_occ = 1;
   static size_t c_smem = 0;
   if (threads != c_threads || smem != c_smem) {
     int occ = 0;
-    cudaError_t qe;
-    if constexpr (PT == kPipe)
-      qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_pipe_kernel<Op, B, U, SM>, threads, smem);
-    else
-      qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U, SM, PT>, threads, smem);
-    if (qe !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<Op, B, U, SM, PT>, threads, smem) !=
             cudaSuccess || occ < 1) {
       (void)cudaGetLastError();
       occ = 1;
@@ -301,8 +186,7 @@ int launch_u(WalkArgs a, const Op& op, int threads, size_t smem, cudaStream_t st
     gp_set_error("%s: grid too large", what);
     return GP_EINVAL;
   }
-  if constexpr (PT == kPipe) walk_pipe_kernel<Op, B, U, SM><<<(unsigned)grid, threads, smem, st>>>(a, op);
-  else walk_kernel<Op, B, U, SM, PT><<<(unsigned)grid, threads, smem, st>>>(a, op);
+  walk_kernel<Op, B, U, SM, PT><<<(unsigned)grid, threads, smem, st>>>(a, op);
   return gp_cuda_fail(cudaGetLastError(), what);
 }
 
@@ -324,7 +208,6 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
   int U = t.unroll >= 4 ? 4 : 2;
   if (sizeof(B) == 8 && U > 2) U = 2;
   if (U > Op::kMaxUnroll && !f32) U = Op::kMaxUnroll;  // the float32-only variants are leaner
-  if (f32 && g_gp_tuning.pipeline && U > Op::kMaxUnrollPipe) U = Op::kMaxUnrollPipe;
 
   WalkArgs a;
   a.csum = d_csum;
@@ -338,15 +221,12 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
 
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = op.s.mode;
-  const bool pipe = g_gp_tuning.pipeline != 0;
 #define GP_LAUNCH(UU)                                                              \
   switch (mode) {                                                                  \
-    case 0: return !f32 ? launch_u<Op, B, UU, 0, 0>(a, op, threads, smem, st, what)               \
-                 : pipe ? launch_u<Op, B, UU, 0, kPipe>(a, op, threads, smem, st, what)           \
-                        : launch_u<Op, B, UU, 0, GP_F32>(a, op, threads, smem, st, what);         \
-    case 1: return !f32 ? launch_u<Op, B, UU, 1, 0>(a, op, threads, smem, st, what)               \
-                 : pipe ? launch_u<Op, B, UU, 1, kPipe>(a, op, threads, smem, st, what)           \
-                        : launch_u<Op, B, UU, 1, GP_F32>(a, op, threads, smem, st, what);         \
+    case 0: return f32 ? launch_u<Op, B, UU, 0, GP_F32>(a, op, threads, smem, st, what)  \
+                       : launch_u<Op, B, UU, 0, 0>(a, op, threads, smem, st, what);        \
+    case 1: return f32 ? launch_u<Op, B, UU, 1, GP_F32>(a, op, threads, smem, st, what)  \
+                       : launch_u<Op, B, UU, 1, 0>(a, op, threads, smem, st, what);        \
     default: return launch_u<Op, B, UU, 2, 0>(a, op, threads, smem, st, what);             \
   }
   if (U >= 4) { GP_LAUNCH(4) }

@@ -110,19 +110,8 @@ def main():
 
     if args.quick:
         lib.gp_set_tuning(b'bulk', 0)
-        grid = []
-        for pipe in (1, 0):
-            lib.gp_set_tuning(b'pipeline', pipe)
-            for threads, unroll, ctas in [(256, 4, 8), (256, 2, 8), (512, 2, 8), (128, 4, 8), (128, 2, 8)]:
-                lib.gp_set_tuning(b'threads', threads)
-                lib.gp_set_tuning(b'unroll', unroll)
-                lib.gp_set_tuning(b'ctas_per_sm', ctas)
-                msg = 'pipe%d t%3d u%d |' % (pipe, threads, unroll)
-                for kind in ['pack', 'unpack', 'sgd', 'sgd_wg', 'adam', 'adam_wg']:
-                    med, best = time_kind(kind)
-                    gbs = bytes_per_elem[kind] * n / med / 1e3
-                    msg += ' %s %6.1fus %4.0f (%.2f)' % (kind, med, gbs, gbs / peak)
-                print(msg, flush=True)
+        grid = [(256, 4, 16, 1), (256, 2, 16, 1), (512, 4, 16, 1), (512, 2, 16, 1), (128, 4, 16, 1),
+                (128, 2, 16, 1), (256, 4, 2, 1), (256, 2, 4, 1), (256, 4, 0, 0), (256, 2, 0, 0)]
     else:
         grid = list(itertools.product([128, 256, 512], [1, 2, 4], [2, 4, 8, 16], [1])) + \
             list(itertools.product([128, 256, 512], [1, 2, 4], [0], [0]))
