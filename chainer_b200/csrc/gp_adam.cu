@@ -39,7 +39,8 @@ template <> struct AdamT<double> { using type = double; };
 
 template <bool AMS>
 struct AdamOp {
-  static constexpr int kMaxUnroll = 2;
+  static constexpr int kMaxUnroll = 4;
+  static constexpr int kDefaultUnroll = 2;
   const void* buffer;
   ScaleArg s;
   double alpha_t, omb1, omb2, eps, eta, wd, lower, upper;

@@ -22,6 +22,7 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // buffer[buf_off + k] = (B)(scale * ptr0[k])
 struct PackOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kDefaultUnroll = 4;
   void* buffer;
   ScaleArg s;
 
@@ -101,6 +102,7 @@ struct PackOp {
 // ptr0[k] = (P)( (B)(scale * buffer[buf_off + k]) )
 struct UnpackOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kDefaultUnroll = 4;
   const void* buffer;
   ScaleArg s;
 

@@ -28,7 +28,7 @@ int gp_cuda_fail(cudaError_t e, const char* what) {
 }
 
 // defaults: see DESIGN.md "tuning"
-GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 4, /*ctas_per_sm*/ 8, /*persistent*/ 1,
+GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 0, /*ctas_per_sm*/ 16, /*persistent*/ 0,
                         /*bn_threads*/ 256, /*pipeline*/ 1};
 
 gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 0, /*tile*/ 4096, /*stages*/ 4, /*ctas*/ 1, /*debug*/ 0, /*chunk*/ 2048};

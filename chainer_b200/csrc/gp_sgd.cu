@@ -36,6 +36,7 @@ template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
 // ------------------------------------------------------------ MomentumSGD --
 struct SgdOp {
   static constexpr int kMaxUnroll = 4;
+  static constexpr int kDefaultUnroll = 2;
   const void* buffer;
   ScaleArg s;
   double lr, momentum;

@@ -205,7 +205,8 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
   if (threads < 32) threads = 32;
   if (threads > kMaxThreads) threads = kMaxThreads;
   threads &= ~31;
-  int U = t.unroll >= 4 ? 4 : 2;
+  // unroll 0 = the op's tuned default
+  int U = t.unroll <= 0 ? Op::kDefaultUnroll : (t.unroll >= 4 ? 4 : 2);
   if (sizeof(B) == 8 && U > 2) U = 2;
   if (U > Op::kMaxUnroll && !f32) U = Op::kMaxUnroll;  // the float32-only variants are leaner
 

@@ -47,9 +47,10 @@ class _Buf(object):
         return self.t.data_ptr()
 
 
-@pytest.fixture(params=[(256, 4, 1, 1, 2048, 4), (128, 1, 1, 0, 2048, 4), (512, 2, 0, 1, 512, 2),
-                        (256, 4, 0, 1, 4096, 3)],
-                ids=['t256u4p-bulk', 't128u1p-nobulk', 't512u2np-bulk512x2', 't256u4np-bulk4096x3'])
+@pytest.fixture(params=[(256, 0, 0, 0, 4096, 4), (256, 4, 1, 1, 2048, 4), (128, 2, 1, 0, 2048, 4),
+                        (512, 2, 0, 1, 512, 2), (256, 4, 0, 1, 4096, 3)],
+                ids=['default', 't256u4p-bulk', 't128u2p-nobulk', 't512u2np-bulk512x2',
+                     't256u4np-bulk4096x3'])
 def tuning(request):
     """(threads, unroll, persistent) of the register-path walker and
     (enable, tile, stages) of the TMA-staged kernels."""
@@ -64,10 +65,10 @@ def tuning(request):
     lib.gp_set_tuning(b'bulk_stages', stages)
     yield request.param
     lib.gp_set_tuning(b'threads', 256)
-    lib.gp_set_tuning(b'unroll', 4)
-    lib.gp_set_tuning(b'persistent', 1)
-    lib.gp_set_tuning(b'bulk', 1)
-    lib.gp_set_tuning(b'bulk_tile', 2048)
+    lib.gp_set_tuning(b'unroll', 0)
+    lib.gp_set_tuning(b'persistent', 0)
+    lib.gp_set_tuning(b'bulk', 0)
+    lib.gp_set_tuning(b'bulk_tile', 4096)
     lib.gp_set_tuning(b'bulk_stages', 4)
 
 

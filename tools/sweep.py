@@ -110,8 +110,8 @@ def main():
 
     if args.quick:
         lib.gp_set_tuning(b'bulk', 0)
-        grid = [(256, 4, 16, 1), (256, 2, 16, 1), (512, 4, 16, 1), (512, 2, 16, 1), (128, 4, 16, 1),
-                (128, 2, 16, 1), (256, 4, 2, 1), (256, 2, 4, 1), (256, 4, 0, 0), (256, 2, 0, 0)]
+        grid = [(256, 0, 0, 0), (128, 2, 0, 0), (128, 4, 0, 0), (256, 2, 0, 0), (256, 4, 0, 0), (384, 2, 0, 0),
+                (512, 2, 0, 0), (512, 4, 0, 0), (256, 2, 16, 1)]
     else:
         grid = list(itertools.product([128, 256, 512], [1, 2, 4], [2, 4, 8, 16], [1])) + \
             list(itertools.product([128, 256, 512], [1, 2, 4], [0], [0]))
