@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--no-write-grad', action='store_true',
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
+    ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
     ap.add_argument('--cpu-seconds', type=float, default=10.0,
                     help='budget of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -239,6 +240,8 @@ def b200_main(args):
 
     comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=adt)
     comm.write_grad = write_grad
+    if args.no_p2p:
+        comm.use_p2p = False
     if args.bucket_mb is not None:
         comm.bucket_bytes = int(args.bucket_mb * (1 << 20))
 
@@ -355,6 +358,8 @@ def b200_main(args):
                                 n_sets),
             'api': 'create_multi_node_optimizer(MomentumSGD|Adam, pure_nccl).update()',
             'bucket_bytes': comm.bucket_bytes if world > 1 else None,
+            'allreduce_impl': (None if world == 1 else
+                               ('peer-memory kernel (gp_p2p)' if comm._p2p is not None else 'nccl')),
         },
         'roofline': {
             'bound': 'hbm', 'kernel': kern['update_kernel'], 'achieved': achieved, 'peak': peak,

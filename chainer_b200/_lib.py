@@ -102,6 +102,15 @@ PROTOTYPES = {
     'gp_nccl_mem_free': (c_int, [c_void_p]),
     'gp_nccl_comm_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p)]),
     'gp_nccl_comm_deregister': (c_int, [c_void_p, c_void_p]),
+    'gp_ipc_get_handle': (c_int, [c_void_p, c_char_p]),
+    'gp_ipc_open_handle': (c_int, [c_char_p, _P(c_void_p)]),
+    'gp_ipc_close_handle': (c_int, [c_void_p]),
+    'gp_p2p_flag_bytes': (c_size_t, []),
+    'gp_p2p_create': (c_int, [_P(c_void_p), c_int, c_int, _P(c_void_p), _P(c_void_p)]),
+    'gp_p2p_set_buffers': (c_int, [c_void_p, _P(c_void_p)]),
+    'gp_p2p_destroy': (c_int, [c_void_p]),
+    'gp_p2p_allreduce': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    'gp_p2p_set_tuning': (c_int, [c_int, c_int]),
     'gp_set_tuning': (c_int, [c_char_p, c_int]),
     'gp_get_tuning': (c_int, [c_char_p, _P(c_int)]),
 }
@@ -109,10 +118,11 @@ PROTOTYPES = {
 # entry points that launch exactly one of OUR kernels (counted in `launches`)
 KERNEL_FUNCS = frozenset([
     'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
-    'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var'])
+    'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
+    'gp_p2p_allreduce'])
 
 # functions whose int return value is an error code
-_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes'}
+_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes'}
 
 
 class GradpathError(RuntimeError):

@@ -96,7 +96,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self.params_data = None
 
         # B200 additions (not configs of the reference)
-        self.bucket_bytes = 32 << 20     # allreduce bucket size when size > 1
+        self.bucket_bytes = 256 << 20    # NCCL path: allreduce bucket size when size > 1
         self.write_grad = True           # fused update keeps param.grad observable
         self._comm_stream = None
         self._events = []
@@ -105,6 +105,8 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self._table_fused = None
         self._finite_flag = None
         self._fused_plan = None
+        self.use_p2p = None              # None: decide at first use; True/False: forced
+        self._p2p = None
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -114,6 +116,9 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             if self._comm_stream is not None:
                 self._comm_stream.synchronize()
             self.mpi_comm.barrier()
+            if self._p2p is not None:
+                self._p2p.destroy()
+                self._p2p = None
             self.nccl_comm.destroy()
             self.nccl_comm = None
 
@@ -124,6 +129,32 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             self.nccl_comm = _SelfNcclComm()
         else:
             self.nccl_comm = _communication_utility.init_nccl_comm(self.mpi_comm)
+            self._init_p2p()
+
+    def _init_p2p(self):
+        """Peer-memory allreduce (csrc/gp_p2p.cu) when all ranks share one box."""
+        from chainer_b200.communicators import _p2p
+        want = self.use_p2p
+        if want is None:
+            want = _p2p.enabled_by_env() and not _lib.get().accepts_host_pointers
+        ok = bool(want) and self.size in (2, 4, 8) and self.intra_size == self.size
+        # the decision must be collective
+        ok = all(self.mpi_comm.allgather(ok))
+        if not ok:
+            self._p2p = None
+            return
+        try:
+            p2p = _p2p.PeerAllreduce(self.mpi_comm)
+            good = True
+        except Exception as e:       # no peer access between these devices
+            warnings.warn('peer-memory allreduce unavailable, using NCCL: {}'.format(e))
+            p2p, good = None, False
+        if all(self.mpi_comm.allgather(good)):
+            self._p2p = p2p
+        else:
+            if p2p is not None:
+                p2p._close(p2p._flag_maps)
+            self._p2p = None
 
     def set_config(self, name, value=True, **kwargs):
         if name == 'allreduce_grad_dtype':
@@ -259,6 +290,16 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             # would copy A to B here)
             self.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM,
                                      stream.ptr)
+            if debug:
+                self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
+            consume(0, n)
+            return
+        if self._p2p is not None:
+            # ONE kernel per rank reduces over NVLink peer memory; the cross-GPU
+            # barriers are inside it, so everything stays on `stream`
+            self._p2p.ensure(buf, stream)
+            _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+            self._p2p.allreduce(dtype, 0, n, stream)
             if debug:
                 self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
             consume(0, n)

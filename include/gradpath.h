@@ -253,6 +253,32 @@ int gp_nccl_mem_free(void* ptr);
 int gp_nccl_comm_register(void* comm, void* buffer, size_t nbytes, void** handle);
 int gp_nccl_comm_deregister(void* comm, void* handle);
 
+/* ------------------------------------------- peer-memory allreduce (NVLink) -- */
+/*
+ * Allreduce of the packed buffer written as ONE kernel per rank over NVLink
+ * peer memory (csrc/gp_p2p.cu): rank r loads the N copies of its 1/N shard (its
+ * own from HBM, N-1 through NVLink), adds them in rank order and stores the sum
+ * into all N buffers; the "everyone has packed" / "everyone has stored" barriers
+ * are flags in peer memory inside the kernel.  Replaces
+ * `nccl_comm.allReduce(...)` (pure_nccl_communicator.py:180-182) when all ranks
+ * share one NVSwitch box (n_ranks 2, 4 or 8).  Buffers and flag blocks are
+ * cudaMalloc allocations exchanged with gp_ipc_* over the control plane.
+ * Sums are formed in rank order with every partial sum rounded to the buffer
+ * dtype, so the result is deterministic and identical on all ranks.
+ */
+#define GP_IPC_HANDLE_BYTES 64
+int gp_ipc_get_handle(void* device_ptr, char* handle64);
+int gp_ipc_open_handle(const char* handle64, void** device_ptr);
+int gp_ipc_close_handle(void* device_ptr);
+size_t gp_p2p_flag_bytes(void); /* size of one rank's (zero-initialised) flag block */
+/* buffers[k] / flags[k]: this process's mapping of rank k's packed buffer / flag block */
+int gp_p2p_create(void** comm, int rank, int n_ranks, void* const* buffers, void* const* flags);
+int gp_p2p_set_buffers(void* comm, void* const* buffers);
+int gp_p2p_destroy(void* comm);
+/* in-place sum over ranks of elements [offset, offset + n_elems) of the buffers */
+int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elems, void* stream);
+int gp_p2p_set_tuning(int ctas, int threads);
+
 /* ---------------------------------------------------------------- tuning -- */
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking
  * sweeps; defaults are the tuned values recorded in DESIGN.md. */

@@ -31,6 +31,36 @@ def main():
     comm = chainer_b200.create_communicator('pure_nccl')
     assert comm.size == world and comm.rank == rank and comm.intra_size == world
 
+    # ---- peer-memory allreduce kernel vs the oracle (rank-order sums): bit-exact ----
+    comm._init_comms()
+    if os.environ.get('CHAINER_B200_P2P', '1') != '0':
+        assert comm._p2p is not None, 'peer-memory allreduce should be active on one box'
+        from chainer_b200.communicators._memory_utility import DeviceMemory
+        from chainer_b200 import _lib
+        lib = _lib.get()
+        for dt_name, tdt, odt in (('float32', torch.float32, np.float32),
+                                  ('float16', torch.float16, np.float16),
+                                  ('bfloat16', torch.bfloat16, og.BF16),
+                                  ('float64', torch.float64, np.float64)):
+            for n in (1, 7, 4096, 100003, 3000000):
+                isz = 8 if dt_name == 'float64' else (4 if dt_name == 'float32' else 2)
+                mem = DeviceMemory()
+                mem.assign(n * isz)
+                comm._p2p.ensure(mem)
+                parts = [og.cast(np.random.default_rng(50 + r).standard_normal(n) * (r + 1), odt)
+                         for r in range(world)]
+                mine = t(parts[rank]).to(tdt)
+                lib.gp_memcpy_async(mem.ptr(), mine.data_ptr(), n * isz, 2, 0)
+                comm._p2p.allreduce(odt, 0, n, None)
+                out = torch.empty(n, dtype=tdt, device='cuda')
+                lib.gp_memcpy_async(out.data_ptr(), mem.ptr(), n * isz, 2, 0)
+                torch.cuda.synchronize()
+                want = og.allreduce_sum(parts, odt)
+                got = out.float().cpu().numpy() if dt_name == 'bfloat16' else out.cpu().numpy()
+                assert np.array_equal(got.view(np.uint8), np.asarray(want).view(np.uint8)), \
+                    ('p2p allreduce', dt_name, n)
+        dist.barrier()
+
     # ---- bcast_data + mean_grad analytic vectors -----------------------------
     plist = [('/a/W', (3, 2)), ('/a/b', (3,)), ('/b/W', (4, 3)), ('/b/b', (4,)), ('/c/b', (5,))]
     fills = [0, 0, 1, 1, 2]
@@ -88,8 +118,10 @@ def main():
                 else:
                     og.adam_update_gpu(q, g, s['m'], s['v'], step)
                 got = p.data.cpu().numpy()
-                if world == 2 and adt is None:
-                    assert np.array_equal(got, q), (opt_name, name, step)   # 2-rank sum is exact
+                if adt is None and (world == 2 or comm._p2p is not None):
+                    # 2-term sums are order-free; the peer-memory kernel adds in rank
+                    # order like the oracle: bit-exact for every world size
+                    assert np.array_equal(got, q), (opt_name, name, step)
                 else:
                     np.testing.assert_allclose(got, q, rtol=tol, atol=tol * 1e-2)
                 np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=tol, atol=1e-8)

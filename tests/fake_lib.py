@@ -329,6 +329,9 @@ class FakeLib(object):
     def gp_nccl_reduce(self, comm, send, recv, count, dtype, op, root, stream):
         return self.gp_nccl_allreduce(comm, send, recv, count, dtype, op, stream)
 
+    def gp_p2p_flag_bytes(self):
+        return 96
+
     def gp_nccl_group_start(self):
         return 0
 

@@ -480,5 +480,7 @@ def test_bucket_bounds():
     assert all(x % 1024 == 0 for x in b[:-1])
     assert all(b[i] < b[i + 1] for i in range(len(b) - 1))
     assert len(b) - 1 == 3                              # 102 MB / 32 MB -> 3 buckets (+ folded tail)
+    comm.bucket_bytes = 256 << 20
+    assert comm._bucket_bounds(25557096, 4) == [0, 25557096]   # default: one allreduce
     M.size = 1
     assert comm._bucket_bounds(1000, 4) == [0, 1000]

@@ -26,14 +26,17 @@ def _free_port():
     return port
 
 
+@pytest.mark.parametrize('p2p', ['1', '0'], ids=['peer-memory', 'nccl'])
 @pytest.mark.parametrize('world_size', [2, 4, 8])
-def test_multi_gpu_path(world_size):
+def test_multi_gpu_path(world_size, p2p):
     if _n_gpus() < world_size:
         pytest.skip('needs {} GPUs'.format(world_size))
+    env = dict(os.environ)
+    env['CHAINER_B200_P2P'] = p2p
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node', str(world_size), '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', '_dist_gpu_worker.py')]
-    out = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+    out = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          timeout=900, text=True)
     assert out.returncode == 0, out.stdout[-6000:]
     for r in range(world_size):
