@@ -44,6 +44,8 @@ def parse_args():
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
     ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
+    ap.add_argument('--p2p-chunk-mb', type=float, default=None)
+    ap.add_argument('--p2p-ctas', type=int, default=None)
     ap.add_argument('--cpu-seconds', type=float, default=10.0,
                     help='budget of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -242,6 +244,10 @@ def b200_main(args):
     comm.write_grad = write_grad
     if args.no_p2p:
         comm.use_p2p = False
+    if args.p2p_chunk_mb is not None:
+        comm.p2p_chunk_bytes = int(args.p2p_chunk_mb * (1 << 20))
+    if args.p2p_ctas is not None:
+        lib.gp_p2p_set_tuning(args.p2p_ctas, 512, 1)
     if args.bucket_mb is not None:
         comm.bucket_bytes = int(args.bucket_mb * (1 << 20))
 
@@ -432,15 +438,22 @@ def time_allreduce(torch, dist, comm, n, bsz, world):
     from chainer_b200.communicators import _communication_utility as cu
     buf = comm.gpu_buffer_a
     type_id = 7 if bsz == 4 else 6
+    dt = np.float32 if bsz == 4 else np.float16
+    if comm._p2p is not None:
+        def one():
+            comm._p2p.allreduce(dt, 0, n, None)
+    else:
+        def one():
+            comm.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM, 0)
     for _ in range(3):
-        comm.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM, 0)
+        one()
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
     e0.record()
     for _ in range(reps):
-        comm.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM, 0)
+        one()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
@@ -450,7 +463,8 @@ def time_allreduce(torch, dist, comm, n, bsz, world):
     S = n * bsz
     alg = S / us / 1e3
     busbw = alg * 2 * (world - 1) / world
-    return {'bytes': S, 'us': us, 'alg_gbs': alg, 'bus_gbs': busbw,
+    return {'impl': 'peer-memory kernel' if comm._p2p is not None else 'nccl',
+            'bytes': S, 'us': us, 'alg_gbs': alg, 'bus_gbs': busbw,
             'frac_of_900': busbw / 900.0, 'frac_of_measured_725': busbw / 725.0}
 
 

@@ -110,7 +110,7 @@ PROTOTYPES = {
     'gp_p2p_set_buffers': (c_int, [c_void_p, _P(c_void_p)]),
     'gp_p2p_destroy': (c_int, [c_void_p]),
     'gp_p2p_allreduce': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p]),
-    'gp_p2p_set_tuning': (c_int, [c_int, c_int]),
+    'gp_p2p_set_tuning': (c_int, [c_int, c_int, c_int]),
     'gp_set_tuning': (c_int, [c_char_p, c_int]),
     'gp_get_tuning': (c_int, [c_char_p, _P(c_int)]),
 }

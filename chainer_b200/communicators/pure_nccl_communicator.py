@@ -106,6 +106,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self._finite_flag = None
         self._fused_plan = None
         self.use_p2p = None              # None: decide at first use; True/False: forced
+        self.p2p_chunk_bytes = 32 << 20  # peer-memory path: pipeline chunk (0: one kernel)
         self._p2p = None
 
     # ------------------------------------------------------------ lifecycle --
@@ -295,14 +296,40 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             consume(0, n)
             return
         if self._p2p is not None:
-            # ONE kernel per rank reduces over NVLink peer memory; the cross-GPU
-            # barriers are inside it, so everything stays on `stream`
+            # ONE kernel per rank and chunk reduces over NVLink peer memory (the
+            # cross-GPU barriers are inside it).  The chunks are pipelined: the
+            # NVLink-bound reduction of chunk i runs on a side stream, on a few
+            # CTAs, under the HBM-bound pack of chunk i+1 and update of chunk i-1.
             self._p2p.ensure(buf, stream)
-            _memory_utility._batched_pack_params(pd, buf, dtype, stream)
-            self._p2p.allreduce(dtype, 0, n, stream)
-            if debug:
-                self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
-            consume(0, n)
+            per = max(self.p2p_chunk_bytes // itemsize, 4096) // 4096 * 4096
+            cb = list(range(0, n, per)) + [n] if self.p2p_chunk_bytes > 0 else [0, n]
+            if len(cb) > 2 and cb[-1] - cb[-2] < per // 2:
+                del cb[-2]
+            if len(cb) == 2:
+                _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+                self._p2p.allreduce(dtype, 0, n, stream)
+                if debug:
+                    self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
+                consume(0, n)
+                return
+            if self._comm_stream is None:
+                self._comm_stream = _dev.Stream(non_blocking=True)
+            cs = self._comm_stream
+            for b in range(len(cb) - 1):
+                lo, hi = cb[b], cb[b + 1]
+                _memory_utility._batched_pack_params(pd, buf, dtype, stream, elem_begin=lo,
+                                                     elem_end=hi)
+                ev = self._event(2 * b)
+                ev.record(stream)
+                cs.wait_event(ev)
+                self._p2p.allreduce(dtype, lo, hi - lo, cs)
+                self._event(2 * b + 1).record(cs)
+            for b in range(len(cb) - 1):
+                stream.wait_event(self._event(2 * b + 1))
+                if debug:
+                    self._ensure_all_finite_device(buf.ptr() + cb[b] * itemsize, dtype,
+                                                   cb[b + 1] - cb[b], stream)
+                consume(cb[b], cb[b + 1])
             return
         if self._comm_stream is None:
             self._comm_stream = _dev.Stream(non_blocking=True)

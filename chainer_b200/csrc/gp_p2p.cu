@@ -118,21 +118,39 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// Data accesses.  Every address is read once and written once per kernel and
+// the barriers order them against the other ranks, so plain (weak) accesses are
+// sufficient; MODE 1 keeps system-scope relaxed accesses for comparison.
+template <int MODE>
 __device__ __forceinline__ uint4 ld_peer(const uint4* p) {
   uint4 v;
-  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p)
-               : "memory");
+  if constexpr (MODE == 1) {
+    asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+  } else {
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+  }
   return v;
 }
+template <int MODE>
 __device__ __forceinline__ void st_peer(uint4* p, const uint4& v) {
-  asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
-               "r"(v.z), "r"(v.w)
-               : "memory");
+  if constexpr (MODE == 1) {
+    asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+  } else {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+  }
 }
 
-template <class T, int N>
+template <class T, int N, int MODE>
 __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   constexpr int E = Vec16<T>::kElems;
   // ---- barrier 1: every rank has finished writing (packing) its buffer ------
@@ -153,7 +171,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
       const int64_t v = v0 + u * stride;
       if (v < v_end) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) x[u][k] = ld_peer(reinterpret_cast<const uint4*>(a.bufs[k]) + v);
+        for (int k = 0; k < N; ++k) x[u][k] = ld_peer<MODE>(reinterpret_cast<const uint4*>(a.bufs[k]) + v);
       }
     }
 #pragma unroll
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
 #pragma unroll
         for (int k = 1; k < N; ++k) Vec16<T>::add(acc, x[u][k]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) st_peer(reinterpret_cast<uint4*>(a.bufs[k]) + v, acc);
+        for (int k = 0; k < N; ++k) st_peer<MODE>(reinterpret_cast<uint4*>(a.bufs[k]) + v, acc);
       }
     }
   }
@@ -181,11 +199,15 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   }
 
   // ---- barrier 2: every rank's stores have landed everywhere ----------------
-  __threadfence_system();
+  // bar.sync orders the CTA's stores before thread 0's system-scope fence, which
+  // is cumulative: one fence per CTA instead of one per thread.
   __syncthreads();
   __shared__ bool last;
   uint32_t* counter = a.flags[a.rank] + 2 * kMaxRanks;
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!last) return;
   if (threadIdx.x == 0) *counter = 0;
@@ -194,21 +216,32 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   wait_all(a, 1, a.epoch);
 }
 
+int g_p2p_ctas = 0;     // 0: default
+int g_p2p_threads = 512;
+int g_p2p_mode = 1;      // system-scope relaxed accesses measured faster (tools/p2p_bench.py)
+
 template <class T>
 int launch_n(const P2PArgs& a, int grid, int threads, cudaStream_t st) {
+  const bool sys = g_p2p_mode == 1;
   switch (a.n) {
-    case 2: p2p_allreduce_kernel<T, 2><<<grid, threads, 0, st>>>(a); break;
-    case 4: p2p_allreduce_kernel<T, 4><<<grid, threads, 0, st>>>(a); break;
-    case 8: p2p_allreduce_kernel<T, 8><<<grid, threads, 0, st>>>(a); break;
+    case 2:
+      if (sys) p2p_allreduce_kernel<T, 2, 1><<<grid, threads, 0, st>>>(a);
+      else p2p_allreduce_kernel<T, 2, 0><<<grid, threads, 0, st>>>(a);
+      break;
+    case 4:
+      if (sys) p2p_allreduce_kernel<T, 4, 1><<<grid, threads, 0, st>>>(a);
+      else p2p_allreduce_kernel<T, 4, 0><<<grid, threads, 0, st>>>(a);
+      break;
+    case 8:
+      if (sys) p2p_allreduce_kernel<T, 8, 1><<<grid, threads, 0, st>>>(a);
+      else p2p_allreduce_kernel<T, 8, 0><<<grid, threads, 0, st>>>(a);
+      break;
     default:
       gp_set_error("gp_p2p_allreduce: world size %d is not supported (2, 4, 8)", a.n);
       return GP_EINVAL;
   }
   return gp_cuda_fail(cudaGetLastError(), "p2p_allreduce_kernel launch");
 }
-
-int g_p2p_ctas = 0;     // 0: default
-int g_p2p_threads = 512;
 
 }  // namespace
 
@@ -298,7 +331,7 @@ int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elem
   a.end = (c->rank == c->n - 1) ? n_elems : ve * E;
   if (c->rank == c->n - 1 && ve < n_vec) a.end = n_elems;
   const int threads = g_p2p_threads;
-  int64_t grid = g_p2p_ctas > 0 ? g_p2p_ctas : gp_sm_count_cached();
+  int64_t grid = g_p2p_ctas > 0 ? g_p2p_ctas : 2 * gp_sm_count_cached();
   const int64_t need = ((ve - vb) + threads - 1) / threads;
   if (grid > need) grid = need > 0 ? need : 1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -313,9 +346,10 @@ int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elem
   }
 }
 
-int gp_p2p_set_tuning(int ctas, int threads) {
+int gp_p2p_set_tuning(int ctas, int threads, int mode) {
   g_p2p_ctas = ctas;
   if (threads >= 32 && threads <= 512) g_p2p_threads = threads & ~31;
+  g_p2p_mode = mode;
   return 0;
 }
 

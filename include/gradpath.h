@@ -277,7 +277,7 @@ int gp_p2p_set_buffers(void* comm, void* const* buffers);
 int gp_p2p_destroy(void* comm);
 /* in-place sum over ranks of elements [offset, offset + n_elems) of the buffers */
 int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elems, void* stream);
-int gp_p2p_set_tuning(int ctas, int threads);
+int gp_p2p_set_tuning(int ctas, int threads, int mode);
 
 /* ---------------------------------------------------------------- tuning -- */
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking

@@ -1,0 +1,69 @@
+"""Microbenchmark of the peer-memory allreduce kernel vs NCCL (run under torchrun).
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/p2p_bench.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank = int(os.environ['RANK'])
+    world = int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import chainer_b200
+    from chainer_b200 import _lib, nccl
+    from chainer_b200.communicators._memory_utility import DeviceMemory
+    lib = _lib.get()
+    comm = chainer_b200.create_communicator('pure_nccl')
+    comm._init_comms()
+    sizes = [int(x) for x in os.environ.get('P2P_SIZES', '25557096,173300800,1048576,65536').split(',')]
+    for n in sizes:
+        mem = DeviceMemory()
+        mem.assign(n * 4)
+        comm._p2p.ensure(mem)
+        lib.gp_memset_async(mem.ptr(), 0, n * 4, 0)
+
+        def timeit(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        us_nccl = timeit(lambda: comm.nccl_comm.allReduce(mem.ptr(), mem.ptr(), n, 7, nccl.NCCL_SUM, 0))
+        rows = []
+        for mode in (0, 1):
+            for threads in (256, 512):
+                for ctas in (74, 148, 296, 592):
+                    lib.gp_p2p_set_tuning(ctas, threads, mode)
+                    us = timeit(lambda: comm._p2p.allreduce(np.float32, 0, n, None))
+                    rows.append((us, mode, threads, ctas))
+        if rank == 0:
+            S = n * 4
+            f = 2.0 * (world - 1) / world
+            print('n=%d (%.1f MB)  NCCL %.1f us  busBW %.0f GB/s' % (n, S / 1e6, us_nccl, S / us_nccl / 1e3 * f))
+            for us, mode, threads, ctas in sorted(rows)[:6]:
+                print('   p2p mode%d t%d c%d: %.1f us  busBW %.0f GB/s  (x%.2f vs NCCL)' % (
+                    mode, threads, ctas, us, S / us / 1e3 * f, us_nccl / us))
+            print('   worst: %s' % (sorted(rows)[-1],), flush=True)
+    lib.gp_p2p_set_tuning(0, 512, 0)
+    comm.finalize()
+
+
+if __name__ == '__main__':
+    main()
