@@ -111,6 +111,10 @@ PROTOTYPES = {
     'gp_p2p_destroy': (c_int, [c_void_p]),
     'gp_p2p_allreduce': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p]),
     'gp_p2p_set_tuning': (c_int, [c_int, c_int, c_int]),
+    'gp_p2p_small_bytes': (c_size_t, [c_int, c_int64]),
+    'gp_p2p_set_small': (c_int, [c_void_p, _P(c_void_p), _P(c_void_p), c_int64]),
+    'gp_p2p_allreduce_small': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
+                                       c_void_p]),
     'gp_set_tuning': (c_int, [c_char_p, c_int]),
     'gp_get_tuning': (c_int, [c_char_p, _P(c_int)]),
 }
@@ -119,10 +123,10 @@ PROTOTYPES = {
 KERNEL_FUNCS = frozenset([
     'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
-    'gp_p2p_allreduce'])
+    'gp_p2p_allreduce', 'gp_p2p_allreduce_small'])
 
 # functions whose int return value is an error code
-_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes'}
+_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes'}
 
 
 class GradpathError(RuntimeError):

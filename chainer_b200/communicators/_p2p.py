@@ -38,7 +38,24 @@ class PeerAllreduce(object):
         self._buf_alloc = None          # keeps the exported allocation alive
         self._buf_maps = []
         self._buf_ptrs = None
-        self.handle = None
+        # the comm handle exists from the start (packed buffers are attached later)
+        arr_f = (ctypes.c_void_p * self.size)(*self._flag_ptrs)
+        arr_b = (ctypes.c_void_p * self.size)(*([None] * self.size))
+        h = ctypes.c_void_p()
+        lib.gp_p2p_create(ctypes.byref(h), self.rank, self.size, arr_b, arr_f)
+        self.handle = h.value
+        # small-message area (MNBN statistics): capacity 2 * 4096 channels
+        self.small_cap = 8192
+        nb = lib.gp_p2p_small_bytes(self.size, self.small_cap)
+        self._small_alloc = _dev._Allocation(nb)
+        self._small_flag_alloc = _dev._Allocation(nbytes)
+        lib.gp_memset_async(self._small_alloc.ptr, 0, nb, 0)
+        lib.gp_memset_async(self._small_flag_alloc.ptr, 0, nbytes, 0)
+        lib.gp_stream_synchronize(0)
+        sp, self._small_maps = self._exchange(self._small_alloc.ptr)
+        fp, self._small_flag_maps = self._exchange(self._small_flag_alloc.ptr)
+        lib.gp_p2p_set_small(self.handle, (ctypes.c_void_p * self.size)(*sp),
+                             (ctypes.c_void_p * self.size)(*fp), self.small_cap)
 
     # -- IPC plumbing -------------------------------------------------------------
     def _exchange(self, ptr):
@@ -80,17 +97,17 @@ class PeerAllreduce(object):
         self._buf_alloc = alloc
         self._buf_ptrs, self._buf_maps = self._exchange(alloc.ptr)
         arr_b = (ctypes.c_void_p * self.size)(*self._buf_ptrs)
-        if self.handle is None:
-            arr_f = (ctypes.c_void_p * self.size)(*self._flag_ptrs)
-            h = ctypes.c_void_p()
-            lib.gp_p2p_create(ctypes.byref(h), self.rank, self.size, arr_b, arr_f)
-            self.handle = h.value
-        else:
-            lib.gp_p2p_set_buffers(self.handle, arr_b)
+        lib.gp_p2p_set_buffers(self.handle, arr_b)
 
     def allreduce(self, dtype, offset_elems, n_elems, stream):
         self.lib.gp_p2p_allreduce(self.handle, _dev.dtype_id(dtype), offset_elems, n_elems,
                                   _dev.stream_ptr(stream))
+
+    def allreduce_small(self, in_ptr, out_ptr, n_elems, C, scale, stream):
+        """out = scale * sum over ranks of in (float32, n_elems <= small_cap); with
+        C > 0 additionally out[C:] -= out[:C]**2 (mean | var)."""
+        self.lib.gp_p2p_allreduce_small(self.handle, in_ptr, out_ptr, n_elems, C, float(scale),
+                                        _dev.stream_ptr(stream))
 
     def destroy(self):
         if self.handle is not None:
@@ -100,6 +117,9 @@ class PeerAllreduce(object):
             self.handle = None
         self._close(self._buf_maps)
         self._close(self._flag_maps)
+        self._close(self._small_maps)
+        self._close(self._small_flag_maps)
         self._buf_maps, self._flag_maps = [], []
+        self._small_maps, self._small_flag_maps = [], []
         self.mpi_comm.barrier()
         self._buf_alloc = None

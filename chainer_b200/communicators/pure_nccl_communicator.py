@@ -106,7 +106,8 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self._finite_flag = None
         self._fused_plan = None
         self.use_p2p = None              # None: decide at first use; True/False: forced
-        self.p2p_chunk_bytes = 32 << 20  # peer-memory path: pipeline chunk (0: one kernel)
+        self.p2p_chunk_bytes = 0         # peer-memory path: pipeline chunk (0: one kernel; measured best)
+        self.p2p_max_bytes = 256 << 20   # beyond this NCCL (NVLS) is faster on 4/8 GPUs (measured)
         self._p2p = None
 
     # ------------------------------------------------------------ lifecycle --
@@ -295,7 +296,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
             consume(0, n)
             return
-        if self._p2p is not None:
+        if self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
             # ONE kernel per rank and chunk reduces over NVLink peer memory (the
             # cross-GPU barriers are inside it).  The chunks are pipelined: the
             # NVLink-bound reduction of chunk i runs on a side stream, on a few

@@ -37,6 +37,12 @@ struct P2PComm {
   void* bufs[kMaxRanks];       // this process's mappings of every rank's packed buffer
   uint32_t* flags[kMaxRanks];  // every rank's flag block: [2 * kMaxRanks] words + grid counter
   uint32_t epoch;
+  // small-message one-shot allreduce: every rank's receive area
+  // [2 parities][n ranks][small_cap floats] and its flag words [kMaxRanks]
+  float* small_recv[kMaxRanks];
+  uint32_t* small_flags[kMaxRanks];
+  int64_t small_cap;
+  uint32_t small_epoch;
 };
 
 struct P2PArgs {
@@ -216,6 +222,67 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   wait_all(a, 1, a.epoch);
 }
 
+// ---------------------------------------------------------------------------
+// One-shot allreduce for SMALL float32 messages (MultiNodeBatchNormalization's
+// 2C statistics, chainermn/functions/batch_normalization.py:57-60, 83-86): every
+// rank stores its vector into slot [rank] of every peer's receive area, raises a
+// flag, waits for the N flags, then adds the N slots in rank order, applies the
+// 1/size scale and (forward statistics) forms var = sqmean - mean^2 -- the work of
+// allReduce + div_by_size + the var kernel in ONE single-CTA launch whose latency
+// is one NVLink store round.  Receive areas are double-buffered by call parity.
+struct SmallArgs {
+  float* recv[kMaxRanks];
+  uint32_t* flags[kMaxRanks];
+  int rank, n;
+  int64_t cap;
+  uint32_t epoch;
+  const float* in;
+  float* out;
+  int n_elems;
+  int C;         // > 0: out[C + c] = out[C + c] - out[c]^2 after scaling (mean | var)
+  float scale_f;
+  double scale_d;
+  int scale_mode;
+};
+
+__global__ void __launch_bounds__(1024) p2p_small_kernel(const SmallArgs a) {
+  const int par = a.epoch & 1;
+  // 1. my contribution into slot [rank] of every rank (own included)
+  for (int i = threadIdx.x; i < a.n_elems; i += blockDim.x) {
+    const float v = a.in[i];
+    for (int k = 0; k < a.n; ++k)
+      a.recv[k][((int64_t)par * a.n + a.rank) * a.cap + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < a.n) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
+    const uint32_t* f = a.flags[a.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+  // 2. rank-order sum of the N slots, scale (x * (1.0/N) in double or exactly in
+  //    float for 2^-k, one rounding), optional variance
+  const float* mine = a.recv[a.rank] + (int64_t)par * a.n * a.cap;
+  for (int i = threadIdx.x; i < a.n_elems; i += blockDim.x) {
+    float acc = __ldcg(mine + i);
+    for (int k = 1; k < a.n; ++k) acc = __fadd_rn(acc, __ldcg(mine + (int64_t)k * a.cap + i));
+    if (a.scale_mode == 1) acc = __fmul_rn(acc, a.scale_f);
+    else if (a.scale_mode == 2) acc = __double2float_rn(__dmul_rn((double)acc, a.scale_d));
+    a.out[i] = acc;
+  }
+  if (a.C > 0) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const float m = a.out[c];
+      a.out[a.C + c] = __fsub_rn(a.out[a.C + c], __fmul_rn(m, m));
+    }
+  }
+}
+
 int g_p2p_ctas = 0;     // 0: default
 int g_p2p_threads = 512;
 int g_p2p_mode = 1;      // system-scope relaxed accesses measured faster (tools/p2p_bench.py)
@@ -279,6 +346,8 @@ int gp_p2p_create(void** comm, int rank, int n_ranks, void* const* buffers, void
   c->rank = rank;
   c->n = n_ranks;
   c->epoch = 0;
+  c->small_cap = 0;
+  c->small_epoch = 0;
   for (int k = 0; k < n_ranks; ++k) {
     c->bufs[k] = buffers[k];
     c->flags[k] = (uint32_t*)flags[k];
@@ -344,6 +413,59 @@ int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elem
       gp_set_error("gp_p2p_allreduce: unsupported dtype id %d", dtype);
       return GP_EINVAL;
   }
+}
+
+size_t gp_p2p_small_bytes(int n_ranks, int64_t capacity_elems) {
+  return (size_t)2 * n_ranks * capacity_elems * sizeof(float);
+}
+
+int gp_p2p_set_small(void* comm, void* const* recv_areas, void* const* flag_blocks,
+                     int64_t capacity_elems) {
+  P2PComm* c = (P2PComm*)comm;
+  if (!c) return GP_EINVAL;
+  for (int k = 0; k < c->n; ++k) {
+    c->small_recv[k] = (float*)recv_areas[k];
+    c->small_flags[k] = (uint32_t*)flag_blocks[k];
+  }
+  c->small_cap = capacity_elems;
+  c->small_epoch = 0;
+  return 0;
+}
+
+int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elems, int64_t C,
+                           double scale, void* stream) {
+  P2PComm* c = (P2PComm*)comm;
+  if (!c || c->small_cap <= 0) {
+    gp_set_error("gp_p2p_allreduce_small: small-message area not set");
+    return GP_EINVAL;
+  }
+  if (n_elems <= 0) return 0;
+  if (n_elems > c->small_cap || (C > 0 && 2 * C != n_elems)) {
+    gp_set_error("gp_p2p_allreduce_small: %lld elements exceed the capacity %lld (or C mismatch)",
+                 (long long)n_elems, (long long)c->small_cap);
+    return GP_EINVAL;
+  }
+  SmallArgs a;
+  for (int k = 0; k < c->n; ++k) {
+    a.recv[k] = c->small_recv[k];
+    a.flags[k] = c->small_flags[k];
+  }
+  a.rank = c->rank;
+  a.n = c->n;
+  a.cap = c->small_cap;
+  a.epoch = ++c->small_epoch;
+  a.in = (const float*)in;
+  a.out = (float*)out;
+  a.n_elems = (int)n_elems;
+  a.C = (int)C;
+  const ScaleArg s = make_scale(scale);
+  a.scale_f = s.fs;
+  a.scale_d = s.ds;
+  a.scale_mode = s.mode;
+  int threads = 1024;
+  while (threads > 64 && threads / 2 >= n_elems) threads >>= 1;
+  p2p_small_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(a);
+  return gp_cuda_fail(cudaGetLastError(), "p2p_small_kernel launch");
 }
 
 int gp_p2p_set_tuning(int ctas, int threads, int mode) {

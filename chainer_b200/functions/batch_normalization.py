@@ -91,6 +91,15 @@ def _allreduce_in_place(comm, buf, n_elems, dtype, stream_ptr=0):
         comm.nccl_comm.allReduce(ptr, ptr, n_elems, type_id, nccl.NCCL_SUM, stream_ptr)
 
 
+def _small_p2p(comm, gdt, n_elems):
+    """The peer-memory one-shot allreduce, if this message qualifies."""
+    comm._init_comms()
+    p2p = getattr(comm, '_p2p', None)
+    if p2p is None or isinstance(gdt, str) or np.dtype(gdt) != np.float32:
+        return None
+    return p2p if n_elems <= p2p.small_cap else None
+
+
 class _NcclImpl(object):
     """``chainermn/functions/batch_normalization.py:35-93``."""
 
@@ -105,6 +114,13 @@ class _NcclImpl(object):
         buf = _new_like(gamma, 2 * C, gdt)
         lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
+        p2p = _small_p2p(self.comm, gdt, 2 * C)
+        if p2p is not None:
+            # allReduce + div_by_size + var in ONE kernel over NVLink peer memory
+            out = _new_like(gamma, 2 * C, gdt)
+            p2p.allreduce_small(_dev.device_ptr(buf), _dev.device_ptr(out), 2 * C, C,
+                                1.0 / self.comm.size, None)
+            return _halves(out, C)
         _allreduce_in_place(self.comm, buf, 2 * C, gdt)
         mean, var = _halves(buf, C)
         # buf *= 1/size; var = sqmean - mean**2 (written over sqmean)
@@ -122,10 +138,20 @@ class _NcclImpl(object):
                             _dev.device_ptr(x_hat), _dev.dtype_id(_dev.array_dtype(x_hat)),
                             None, None, _lib.GP_F32, N, C, HW, _dev.device_ptr(buf),
                             _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
-        _allreduce_in_place(self.comm, buf, 2 * C, gdt)
-        lib.gp_scale(_dev.device_ptr(buf), _dev.dtype_id(gdt), 2 * C, 1.0 / self.comm.size, 0)
+        buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
         gbeta, ggamma = _halves(buf, C)
         return gbeta, ggamma
+
+    def _mean_over_ranks(self, buf, n, gdt, like):
+        p2p = _small_p2p(self.comm, gdt, n)
+        if p2p is not None:
+            out = _new_like(like, n, gdt)
+            p2p.allreduce_small(_dev.device_ptr(buf), _dev.device_ptr(out), n, 0,
+                                1.0 / self.comm.size, None)
+            return out
+        _allreduce_in_place(self.comm, buf, n, gdt)
+        _lib.get().gp_scale(_dev.device_ptr(buf), _dev.dtype_id(gdt), n, 1.0 / self.comm.size, 0)
+        return buf
 
     def get_ggamma_and_gbeta_from_x(self, axis, gamma, gy, x, mean, inv_std):
         """Same statistics with ``x_hat = (x - mean) * inv_std`` formed on the
@@ -141,8 +167,7 @@ class _NcclImpl(object):
                             _dev.dtype_id(_dev.array_dtype(mean)), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt),
                             _workspace(self.comm, C), 0)
-        _allreduce_in_place(self.comm, buf, 2 * C, gdt)
-        lib.gp_scale(_dev.device_ptr(buf), _dev.dtype_id(gdt), 2 * C, 1.0 / self.comm.size, 0)
+        buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
         gbeta, ggamma = _halves(buf, C)
         return gbeta, ggamma
 

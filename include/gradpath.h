@@ -278,6 +278,19 @@ int gp_p2p_destroy(void* comm);
 /* in-place sum over ranks of elements [offset, offset + n_elems) of the buffers */
 int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elems, void* stream);
 int gp_p2p_set_tuning(int ctas, int threads, int mode);
+/*
+ * One-shot allreduce for small float32 messages (MNBN's 2C statistics,
+ * chainermn/functions/batch_normalization.py:57-60, 83-86): allReduce +
+ * div_by_size (+ `var = sqmean - mean^2` when C > 0, :65-67) in ONE single-CTA
+ * kernel over peer memory.  out[i] = scale * sum_ranks in[i] (rank order);
+ * recv_areas[k] / flag_blocks[k]: mappings of rank k's zero-initialised receive
+ * area (gp_p2p_small_bytes) and flag block (gp_p2p_flag_bytes).
+ */
+size_t gp_p2p_small_bytes(int n_ranks, int64_t capacity_elems);
+int gp_p2p_set_small(void* comm, void* const* recv_areas, void* const* flag_blocks,
+                     int64_t capacity_elems);
+int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elems, int64_t C,
+                           double scale, void* stream);
 
 /* ---------------------------------------------------------------- tuning -- */
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking

@@ -59,6 +59,52 @@ def main():
                 got = out.float().cpu().numpy() if dt_name == 'bfloat16' else out.cpu().numpy()
                 assert np.array_equal(got.view(np.uint8), np.asarray(want).view(np.uint8)), \
                     ('p2p allreduce', dt_name, n)
+        # one-shot small allreduce (MNBN statistics messages): bit-exact, incl. var
+        for C in (1, 3, 64, 257, 2048, 4096):
+            vals = [np.random.default_rng(90 + r).standard_normal(2 * C).astype(np.float32)
+                    for r in range(world)]
+            for use_var in (0, C):
+                src = t(vals[rank])
+                out = torch.empty(2 * C, device='cuda')
+                comm._p2p.allreduce_small(src.data_ptr(), out.data_ptr(), 2 * C, use_var,
+                                          1.0 / world, None)
+                torch.cuda.synchronize()
+                want = og.scale_buffer(og.allreduce_sum(vals, np.float32), np.float32, 1.0 / world)
+                if use_var:
+                    want = want.copy()
+                    want[C:] = want[C:] - np.square(want[:C])
+                assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), \
+                    ('small allreduce', C, use_var)
+        # latency of one MNBN statistics exchange: NCCL allreduce + scale vs one-shot kernel
+        from chainer_b200 import nccl as _nccl
+        C = 256
+        src = torch.randn(2 * C, device='cuda')
+        out = torch.empty(2 * C, device='cuda')
+
+        def lat(fn, reps=200):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / reps
+
+        def via_nccl():
+            comm.nccl_comm.allReduce(src.data_ptr(), out.data_ptr(), 2 * C, 7, _nccl.NCCL_SUM, 0)
+            lib.gp_scale(out.data_ptr(), 7, 2 * C, 1.0 / world, 0)
+            lib.gp_bn_finish_mean_var(out.data_ptr(), 7, C, 1.0, out.data_ptr() + 4 * C, 0)
+
+        def via_p2p():
+            comm._p2p.allreduce_small(src.data_ptr(), out.data_ptr(), 2 * C, C, 1.0 / world, None)
+        a_us, b_us = lat(via_nccl), lat(via_p2p)
+        if rank == 0:
+            print('MNBN statistics exchange (2C = %d floats, %d ranks): NCCL allreduce + scale + var '
+                  '%.1f us, one-shot peer-memory kernel %.1f us' % (2 * C, world, a_us, b_us), flush=True)
         dist.barrier()
 
     # ---- bcast_data + mean_grad analytic vectors -----------------------------
@@ -123,8 +169,13 @@ def main():
                     # order like the oracle: bit-exact for every world size
                     assert np.array_equal(got, q), (opt_name, name, step)
                 else:
-                    np.testing.assert_allclose(got, q, rtol=tol, atol=tol * 1e-2)
-                np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=tol, atol=1e-8)
+                    # NCCL's summation order differs from the oracle's rank order by a
+                    # few ulp of the SUM; Adam divides by sqrt(v) + eps, so elements
+                    # with |g| ~ eps amplify that (d step / d g ~ alpha / eps): judge
+                    # Adam on the mean gradient and allow the amplified step error
+                    atol = tol * 1e-2 if opt_name == 'momentum_sgd' else 2e-4
+                    np.testing.assert_allclose(got, q, rtol=tol, atol=atol)
+                np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=tol, atol=2e-8)
             assert actual.t == step
         # every rank holds identical parameters
         flat = torch.cat([p.data.reshape(-1) for _, p in sorted(m.namedparams())])

@@ -332,6 +332,9 @@ class FakeLib(object):
     def gp_p2p_flag_bytes(self):
         return 96
 
+    def gp_p2p_small_bytes(self, n, cap):
+        return 2 * n * cap * 4
+
     def gp_nccl_group_start(self):
         return 0
 

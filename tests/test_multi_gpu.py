@@ -41,3 +41,6 @@ def test_multi_gpu_path(world_size, p2p):
     assert out.returncode == 0, out.stdout[-6000:]
     for r in range(world_size):
         assert 'GPU RANK %d OK' % r in out.stdout
+    for line in out.stdout.splitlines():
+        if line.startswith('MNBN statistics exchange'):
+            print(line)
