@@ -301,6 +301,7 @@ def b200_main(args):
     for k in range(K):
         step(W + k)
     ev1.record()
+    t_enq = time.perf_counter()
     barrier()
     t1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
@@ -380,6 +381,7 @@ def b200_main(args):
         'clocks': clocks,
         'img_per_s_gradpath_bound': 32.0 * world / (ms_step * 1e-3),
         'host_us_per_step': 1e6 * (t1 - t0) / K,
+        'host_enqueue_us_per_step': 1e6 * (t_enq - t0) / K,
     }
     if bus is not None:
         line['allreduce'] = bus
@@ -473,37 +475,64 @@ def time_e2e(torch, dist, world, opt, params_sorted, p_arena, g_arenas, set_grad
     """Same step through the public API with HOST buffers: every step copies the
     step's gradients from pinned host memory to the device, runs
     optimizer.update(), and reads the updated parameters back to pinned host
-    memory; all inside the timed region."""
-    h_grads = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_grads.copy_(g_arenas[0].cpu())
-    h_params = torch.empty(n, dtype=torch.float32).pin_memory()
+    memory; all inside the timed region.  The copies run on their own streams so
+    that the H2D of step k+1 and the D2H of step k-1 overlap the kernels of step k
+    (PCIe is full duplex); dependencies are expressed with events:
+        H2D(k) -> update(k) -> snapshot(k) -> D2H(k);  H2D(k+2) waits update(k)
+    (two gradient arenas, two parameter snapshots)."""
+    h_grads = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h, g in zip(h_grads, g_arenas):
+        h.copy_(g.cpu())
+    h_params = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    snap = [torch.empty_like(p_arena) for _ in range(2)]
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_h2d = [torch.cuda.Event() for _ in range(2)]
+    ev_upd = [torch.cuda.Event() for _ in range(2)]
+    ev_snap = [torch.cuda.Event() for _ in range(2)]
+    ev_d2h = [torch.cuda.Event() for _ in range(2)]
 
     def one(k):
-        g = g_arenas[k % len(g_arenas)]
-        g.copy_(h_grads, non_blocking=True)            # H2D, pinned
+        i = k % 2
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_upd[i])                 # arena i was consumed by update(k-2)
+            g_arenas[i].copy_(h_grads[i], non_blocking=True)       # H2D, pinned
+            ev_h2d[i].record(s_h2d)
+        main.wait_event(ev_h2d[i])
         set_grads(k)
         opt.update()
-        h_params.copy_(p_arena, non_blocking=True)     # D2H, pinned
+        ev_upd[i].record(main)
+        main.wait_event(ev_d2h[i])                      # snapshot i was read back by D2H(k-2)
+        snap[i].copy_(p_arena)                          # device snapshot of the result
+        ev_snap[i].record(main)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_snap[i])
+            h_params[i].copy_(snap[i], non_blocking=True)          # D2H, pinned
+            ev_d2h[i].record(s_d2h)
     for k in range(warmup):
         one(k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(main)
     for k in range(steps):
-        one(k)
-    e1.record()
+        one(warmup + k)
+    main.wait_event(ev_d2h[0])                          # the end event covers all three streams
+    main.wait_event(ev_d2h[1])
+    e1.record(main)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    assert bool(torch.isfinite(h_params[:1024]).all())
+    assert bool(torch.isfinite(h_params[0][:1024]).all())
     return {'value': world * n * bytes_per_elem_total / (ms * 1e-3) / 1e9, 'unit': 'GB/s',
             'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': n * 4, 'ms_per_step': ms,
-            'steps': steps}
+            'steps': steps,
+            'note': 'H2D(k+1) and D2H(k-1) overlap step k on separate streams; CUDA events, the '
+                    'end event waits for the last D2H copies'}
 
 
 def main():

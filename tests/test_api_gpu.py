@@ -261,3 +261,29 @@ def test_full_size_resnet50_through_api(comm):
         assert torch.equal(p.update_rule.state['v'], -(lr * g)), name
         assert torch.equal(p.data, d0 + (-(lr * g))), name
         assert torch.equal(p.grad, g), name
+
+
+def test_double_buffering_optimizer_on_gpu(comm):
+    """tests/chainermn_tests/optimizer_tests/test_double_buffering_optimizer.py:43-90
+    on the device: the mean lands in communicated_target one call late, computed
+    on the non-blocking side stream."""
+    import torch
+    rng = np.random.default_rng(4)
+    model, host = _model(sorted(PLIST)[:6], rng)
+    actual = chainer_b200.MomentumSGD(lr=0.1)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm, double_buffering=True)
+    opt.setup(model)
+    grads = [np.asarray(rng.standard_normal(a.shape)).astype(np.float32).reshape(a.shape) for a in host]
+    _set_grads(model, grads)
+    opt.update()                                        # bcast + deep copy
+    assert actual.t == 0 and opt.communicated_target is not None
+    _set_grads(model, grads)
+    opt.update()                                        # swap + async mean; no update yet
+    assert actual.t == 0
+    opt.wait()
+    for (_, p), g in zip(sorted(opt.communicated_target.namedparams()), grads):
+        assert_bits_equal(p.grad.cpu().numpy(), g, 'communicated_target grad')
+    _set_grads(model, grads)
+    opt.update()
+    opt.wait()
+    assert actual.t == 1
