@@ -133,6 +133,23 @@ class ParamsData(object):
         self._blob = blob
         return lib
 
+    def clone(self):
+        """A copy with its own host tables and device table (same parameters)."""
+        new = ParamsData.__new__(ParamsData)
+        new.__dict__.update(self.__dict__)
+        new.host_segs = self.host_segs.copy()
+        new.arrays = list(self.arrays)
+        new._table = DeviceTable()
+        new.d_csum = new.d_segs = None
+        return new
+
+    def set_ptr0(self, ptrs, stream=None):
+        """Replace the ptr[0] column (the gradient arrays) and re-upload."""
+        self.host_segs['ptr'][:, 0] = ptrs
+        self._finish_flags()
+        if self.n_params > 0:
+            self.upload(stream)
+
     def layout_hint(self, buf_dtype):
         """layout_hint argument of the fused update kernels for this table."""
         if self.n_params == 0:

@@ -24,6 +24,7 @@ What changes underneath (none of it observable through that surface):
 * ``multi_node_mean_grad_and_update`` additionally fuses the optimizer update
   (MomentumSGD / Adam) into that kernel.
 """
+import collections
 import ctypes
 import warnings
 
@@ -470,8 +471,7 @@ class _FusedPlan(object):
         self.table = _memory_utility.DeviceTable()
         self.pd = _memory_utility.ParamsData(self.params, 'grad', False, extra_ptrs=self.extra,
                                              table=self.table)
-        self.grad_ptrs = self.pd.host_segs['ptr'][:, 0].copy()
-        self.seen = dict((id(g), g) for g in self.pd.arrays[:len(self.params)])
+        self.cache = collections.OrderedDict()
         self.sizes = [_dev.array_size(p.data) for p in self.params]
         self.dtypes = [_dev.array_dtype(p.data) for p in self.params]
         # launch groups: rules with equal hyperparameters and step count.  The
@@ -501,54 +501,57 @@ class _FusedPlan(object):
         return (model is self.model and optimizer is self.optimizer and
                 zero_fill == self.zero_fill and self.versions == _versions())
 
-    def _refresh_grads(self, stream):
-        """Re-read every gradient pointer; re-upload the tables if any moved."""
+    def _tables(self, stream):
+        """Device tables for the CURRENT gradient arrays.
+
+        Chainer reallocates gradients every step (cleargrads), frameworks with
+        persistent gradient buffers do not, and benchmarks rotate a few sets: the
+        tables are cached per tuple of gradient array OBJECTS (the cache holds
+        references, so ids cannot be recycled), up to four sets, each with its own
+        device copy.  A hit costs one tuple of ids; a miss re-reads the pointers,
+        validates new arrays like ParamsData does and uploads one table.
+        """
         params = self.params
         grads = [p.grad for p in params]
-        seen = self.seen
+        ids = tuple(map(id, grads))
+        if _NONE_ID in ids:
+            for i, g in enumerate(grads):
+                if g is None:
+                    g = _dev.zeros_like(params[i].data)      # zero_fill
+                    params[i].grad = g
+                    grads[i] = g
+            ids = tuple(map(id, grads))
+        ent = self.cache.get(ids)
+        if ent is not None:
+            self.cache.move_to_end(ids)
+            return ent
         ptrs = []
         for i, g in enumerate(grads):
-            if g is None:
-                g = _dev.zeros_like(params[i].data)      # zero_fill
-                params[i].grad = g
-                grads[i] = g
-            if id(g) not in seen:
-                # first sight of this array object: validate it like ParamsData does
-                dt = _dev.array_dtype(g)
-                if isinstance(dt, str) or dt != self.dtypes[i]:
-                    if isinstance(dt, str) or dt not in (np.float16, np.float32, np.float64):
-                        raise ValueError('dtype must be float16, float32 or float64.')
-                    self.comm._fused_plan = None
-                    raise _PlanStale()
-                if _dev.array_size(g) != self.sizes[i]:
-                    raise ValueError('gradient of size {} for a parameter of size {}'.format(
-                        _dev.array_size(g), self.sizes[i]))
-                if len(seen) > 8192:
-                    seen.clear()
-                seen[id(g)] = g
-            try:
-                ptrs.append(g.data_ptr())
-            except AttributeError:
-                ptrs.append(_dev.device_ptr(g))
+            dt = _dev.array_dtype(g)
+            if isinstance(dt, str) or dt != self.dtypes[i]:
+                if isinstance(dt, str) or dt not in (np.float16, np.float32, np.float64):
+                    raise ValueError('dtype must be float16, float32 or float64.')
+                self.comm._fused_plan = None
+                raise _PlanStale()
+            if _dev.array_size(g) != self.sizes[i]:
+                raise ValueError('gradient of size {} for a parameter of size {}'.format(
+                    _dev.array_size(g), self.sizes[i]))
+            ptrs.append(_dev.device_ptr(g))
         ptrs = np.asarray(ptrs, dtype=np.uint64)
-        if not np.array_equal(ptrs, self.grad_ptrs):
-            self.grad_ptrs = ptrs
-            self.pd.host_segs['ptr'][:, 0] = ptrs
-            self.pd.arrays[:len(grads)] = grads
-            self.pd._finish_flags()
-            self.pd.upload(stream)
-            for _, idx, sub in self.groups:
-                if idx is not None:
-                    sub.host_segs['ptr'][:, 0] = ptrs[idx]
-                    sub._finish_flags()
-                    sub.upload(stream)
+        if len(self.cache) >= 4:
+            _, ent = self.cache.popitem(last=False)          # recycle the oldest set's tables
+        else:
+            ent = _TableSet(self)
+        ent.update(ptrs, grads, stream)
+        self.cache[ids] = ent
+        return ent
 
     def run(self, stream):
         comm = self.comm
         comm._init_comms()
         dtype = comm._allreduce_dtype()
         try:
-            self._refresh_grads(stream)
+            tables = self._tables(stream)
         except _PlanStale:
             # a gradient changed dtype: rebuild through the slow path
             if not comm.multi_node_mean_grad_and_update(self.model, self.optimizer,
@@ -562,7 +565,7 @@ class _FusedPlan(object):
             rule.t += 1
         for rule in self.rules:
             rule.t += 1
-        pd = self.pd
+        pd = tables.pd
         n_elems = pd.n_elems
         needs_sync = comm._prepare_allreduce_pack_buffer(dtype, n_elems)
         if stream != _dev.Stream.null and needs_sync:
@@ -576,7 +579,7 @@ class _FusedPlan(object):
         buf_ptr = comm.gpu_buffer_a.ptr()
         sp = stream.ptr
         launches = []
-        for rep, idx, t in self.groups:
+        for rep, idx, t in tables.groups:
             key = rep.fused_key()                 # re-read hyperparameters (and alpha_t)
             if key[0] == 'adam':
                 ddt = self.dtypes[0 if idx is None else idx[0]]
@@ -610,6 +613,28 @@ class _FusedPlan(object):
 
 class _PlanStale(Exception):
     pass
+
+
+_NONE_ID = id(None)
+
+
+class _TableSet(object):
+    """Device tables of a fused plan for ONE set of gradient arrays: a copy of the
+    plan's segment tables with its own gradient-pointer column and device memory."""
+
+    def __init__(self, plan):
+        self.pd = plan.pd.clone()
+        self.groups = []
+        for rep, idx, sub in plan.groups:
+            self.groups.append((rep, idx, self.pd if idx is None else sub.clone()))
+        self.grads = None
+
+    def update(self, ptrs, grads, stream):
+        self.grads = grads                       # keep the arrays (and their ids) alive
+        self.pd.set_ptr0(ptrs, stream)
+        for _, idx, sub in self.groups:
+            if idx is not None:
+                sub.set_ptr0(ptrs[idx], stream)
 
 
 def _fusion_plan(model, optimizer, zero_fill):
