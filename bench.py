@@ -346,8 +346,9 @@ def b200_main(args):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        traffic = prof.get('{}_{}_{}'.format(optimizer_name, args.allreduce_dtype,
-                                              'wg' if write_grad else 'nowg'))
+        if args.workload == 'resnet50':       # the ncu capture is of the ResNet-50 list
+            traffic = prof.get('{}_{}_{}'.format(optimizer_name, args.allreduce_dtype,
+                                                  'wg' if write_grad else 'nowg'))
     except Exception:
         pass
 
