@@ -83,6 +83,8 @@ PROTOTYPES = {
     'gp_bn_workspace_bytes': (c_size_t, [c_int64]),
     'gp_bn_fwd_stats': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
                                 c_void_p, c_void_p]),
+    'gp_bn_fwd_mean_var': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
+                                   c_void_p, c_void_p]),
     'gp_bn_bwd_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                 c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     'gp_bn_finish_mean_var': (c_int, [c_void_p, c_int, c_int64, c_double, c_void_p, c_void_p]),
@@ -122,7 +124,7 @@ PROTOTYPES = {
 # entry points that launch exactly one of OUR kernels (counted in `launches`)
 KERNEL_FUNCS = frozenset([
     'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
-    'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
+    'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
     'gp_p2p_allreduce', 'gp_p2p_allreduce_small'])
 
 # functions whose int return value is an error code

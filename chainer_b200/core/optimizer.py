@@ -341,11 +341,20 @@ class GradientMethod(Optimizer):
         self.call_hooks('pre')
 
         self.t += 1
-        for param in self.target.params():
-            param.update()
+        if not self._multi_tensor_update():
+            for param in self.target.params():
+                param.update()
 
         self.reallocate_cleared_grads()
         self.call_hooks('post')
+
+    def _multi_tensor_update(self):
+        """All parameter updates of this step as ONE launch per (dtype, hyperparameter)
+        group instead of one kernel per parameter, when every rule is a stock
+        MomentumSGD / Adam rule without hooks, fp32-update or loss scaling.
+        Returns False (nothing done) otherwise."""
+        from chainer_b200.core import _multi_tensor
+        return _multi_tensor.update(self)
 
     def use_cleargrads(self, use=True):
         warnings.warn('GradientMethod.use_cleargrads is deprecated.', DeprecationWarning)

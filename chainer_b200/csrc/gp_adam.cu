@@ -49,6 +49,15 @@ struct AdamOp {
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype1; }
 
+  // where the (summed) gradient of element e comes from: the packed buffer, or --
+  // stand-alone optimizer.update() without a communicator, buffer == NULL -- the
+  // gradient array itself (then dtype0 == buffer dtype is required by the host)
+  template <class B>
+  __device__ __forceinline__ const B* grad_src(const gp_seg_t& g, int64_t e) const {
+    return buffer ? reinterpret_cast<const B*>(buffer) + g.buf_off + e
+                  : reinterpret_cast<const B*>(g.ptr[0]) + e;
+  }
+
   template <class T> struct Consts { T alpha_t, omb1, omb2, eps, eta, wd, lower, upper; };
   template <class T> __device__ __forceinline__ Consts<T> consts() const {
     Consts<T> c;
@@ -99,7 +108,7 @@ struct AdamOp {
         r.pv[u] = mptr<P>(seg[u]->ptr[3]) + e[u];
         r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
         if constexpr (AMS) r.ph[u] = mptr<P>(seg[u]->ptr[4]) + e[u];
-        r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+        r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
         r.rp[u] = ld4(r.pp[u]);
         r.rm[u] = ld4(r.pm[u]);
         r.rv[u] = ld4(r.pv[u]);
@@ -190,7 +199,7 @@ struct AdamOp {
   __device__ __forceinline__ void one(const gp_seg_t& sg, int64_t e) const {
     using T = typename AdamT<P>::type;
     constexpr bool ams = AMS;
-    const auto xb = to_carrier(reinterpret_cast<const B*>(buffer)[sg.buf_off + e]);
+    const auto xb = to_carrier(*grad_src<B>(sg, e));
     const T g = gpw::mean_grad_value<B, P, SM>(xb, s);
     P* pp = mptr<P>(sg.ptr[1]) + e;
     P* pm = mptr<P>(sg.ptr[2]) + e;
@@ -236,7 +245,7 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
                               double eta, double weight_decay_rate, double lower, double upper,
                               int adam_flags, int write_grad, int layout_hint, void* stream) {
   gpb::BulkArgs a = {};
-  if (layout_hint && n_segs > 0) {
+  if (layout_hint && n_segs > 0 && buffer) {
     a.csum = d_csum; a.segs = d_segs; a.n_segs = n_segs; a.begin = elem_begin; a.end = elem_end;
     a.buffer = buffer;
     const int ps = gp_itemsize(layout_hint);
@@ -254,7 +263,7 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
     AdamOp<true> op;
     fill_adam(op, buffer, scale, alpha_t, one_minus_beta1, one_minus_beta2, eps, eta,
               weight_decay_rate, lower, upper, adam_flags, write_grad);
-    if (layout_hint && n_segs > 0) {
+    if (layout_hint && n_segs > 0 && buffer) {
       const int r = gpb::launch_bulk(buf_dtype, layout_hint, a, op, stream, "gp_unpack_adam");
       if (r <= 0) return r;
     }
@@ -274,7 +283,7 @@ extern "C" int gp_unpack_adam(const void* buffer, int buf_dtype, const int64_t* 
   op.upper = upper;
   op.flags = adam_flags;
   op.write_grad = write_grad;
-  if (layout_hint && n_segs > 0) {
+  if (layout_hint && n_segs > 0 && buffer) {
     const int r = gpb::launch_bulk(buf_dtype, layout_hint, a, op, stream, "gp_unpack_adam");
     if (r <= 0) return r;
   }

@@ -52,6 +52,7 @@ struct BnArgs {
   void* out;
   int out_dtype;
   double out_scale;  // fwd: 1 / (N * HW); bwd: 1
+  int finish_var;    // fwd, one rank: write [mean | var] instead of [mean | sqmean]
 };
 
 // MODE 0: a = sum x, b = sum x^2
@@ -86,20 +87,29 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const BnArgs a) {
     const int total = rows * VR;
     constexpr int UN = 4;
     Acc p0[4] = {0, 0, 0, 0}, p1[4] = {0, 0, 0, 0};
-    for (int base = threadIdx.x; base < total; base += blockDim.x * UN) {
+    // (row, col) of this thread's next vector, advanced incrementally: an integer
+    // division per 16-byte load made the forward kernel instruction-bound
+    const int step = blockDim.x;
+    const int dq = step / VR, dr = step - dq * VR;
+    int row = threadIdx.x / VR, col = threadIdx.x - row * VR;
+    for (int base = threadIdx.x; base < total; base += step * UN) {
       Raw4<TX> rx[UN];
       Raw4<TG> rg[UN];
       bool act[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const int idx = base + u * blockDim.x;
+        const int idx = base + u * step;
         act[u] = idx < total;
         if (act[u]) {
-          const int row = idx / VR;
-          const int col = idx - row * VR;
           const int64_t off = (n0 + row) * row_stride + ch_off + (int64_t)col * 4;
           rx[u] = ld4_stream(x + off);
           if (MODE != 0) rg[u] = ld4_stream(gy + off);
+        }
+        col += dr;
+        row += dq;
+        if (col >= VR) {
+          col -= VR;
+          ++row;
         }
       }
 #pragma unroll
@@ -133,9 +143,10 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const BnArgs a) {
   } else {
     const int HWi = (int)a.HW;
     const int total = rows * HWi;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int row = idx / HWi;
-      const int col = idx - row * HWi;
+    const int step = blockDim.x;
+    const int dq = step / HWi, dr = step - dq * HWi;
+    int row = threadIdx.x / HWi, col = threadIdx.x - row * HWi;
+    for (int idx = threadIdx.x; idx < total; idx += step) {
       const int64_t off = (n0 + row) * row_stride + ch_off + col;
       const Acc v = (Acc)to_carrier(x[off]);
       if (MODE == 0) {
@@ -147,6 +158,12 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const BnArgs a) {
         if (MODE == 2) xh = (xh - mu) * is;
         s0 += g;
         s1 += g * xh;
+      }
+      col += dr;
+      row += dq;
+      if (col >= HWi) {
+        col -= HWi;
+        ++row;
       }
     }
   }
@@ -184,6 +201,26 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const BnArgs a) {
       t1 += __ldcg(part + k * 2 + 1);
     }
     a.counters[c] = 0;  // leave the workspace zeroed for the next call
+  }
+  if (a.finish_var) {
+    // single rank: no allreduce follows, so form var = sqmean - mean^2 here with
+    // the arithmetic of bn_finish_kernel (operands rounded to the output dtype)
+    if (a.out_dtype == GP_F32) {
+      const float m = __double2float_rn(t0 * a.out_scale), q = __double2float_rn(t1 * a.out_scale);
+      reinterpret_cast<float*>(a.out)[c] = m;
+      reinterpret_cast<float*>(a.out)[a.C + c] = __fsub_rn(q, __fmul_rn(m, m));
+    } else if (a.out_dtype == GP_F16) {
+      const float m = __half2float(__double2half(t0 * a.out_scale));
+      const float q = __half2float(__double2half(t1 * a.out_scale));
+      reinterpret_cast<__half*>(a.out)[c] = __float2half_rn(m);
+      reinterpret_cast<__half*>(a.out)[a.C + c] =
+          __float2half_rn(__fsub_rn(q, __half2float(__float2half_rn(__fmul_rn(m, m)))));
+    } else {
+      const double m = t0 * a.out_scale, q = t1 * a.out_scale;
+      reinterpret_cast<double*>(a.out)[c] = m;
+      reinterpret_cast<double*>(a.out)[a.C + c] = __dsub_rn(q, __dmul_rn(m, m));
+    }
+    return;
   }
   store_stat(a.out, a.out_dtype, c, t0 * a.out_scale);
   store_stat(a.out, a.out_dtype, a.C + c, t1 * a.out_scale);
@@ -237,7 +274,7 @@ int launch_x(int x_dtype, int gy_dtype, const BnArgs& a, bool vec, dim3 grid, in
 
 int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype, const void* mean,
               const void* inv_std, int stat_dtype, int64_t N, int64_t C, int64_t HW, void* out,
-              int out_dtype, void* workspace, double out_scale, void* stream) {
+              int out_dtype, void* workspace, double out_scale, void* stream, int finish_var = 0) {
   if (N <= 0 || C <= 0 || HW <= 0) return 0;
   if (out_dtype != GP_F16 && out_dtype != GP_F32 && out_dtype != GP_F64) {
     gp_set_error("gp_bn_stats: unsupported output dtype id %d", out_dtype);
@@ -251,13 +288,14 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
   a.x = x; a.gy = gy; a.mean = mean; a.inv_std = inv_std; a.stat_dtype = stat_dtype;
   a.N = N; a.C = C; a.HW = HW;
   a.out = out; a.out_dtype = out_dtype; a.out_scale = out_scale;
+  a.finish_var = finish_var;
 
-  // splits over the batch axis: enough CTAs to fill the machine (>= 4 per SM)
-  // while keeping >= ~16 KB of rows per CTA.
+  // splits over the batch axis: enough CTAs for ~16 per SM (several waves, so that
+  // the uneven last wave is short) while keeping >= ~8 KB of rows per CTA.
   const int sms = gp_sm_count_cached();
-  int64_t S = (4 * (int64_t)sms + C - 1) / C;
+  int64_t S = (g_gp_tuning.bn_ctas_per_sm * (int64_t)sms + C - 1) / C;
   const int64_t bytes_per_row = HW * gp_itemsize(x_dtype);
-  int64_t max_by_size = (N * bytes_per_row) / 16384;
+  int64_t max_by_size = (N * bytes_per_row) / 8192;
   if (max_by_size < 1) max_by_size = 1;
   if (S > max_by_size) S = max_by_size;
   if (S > N) S = N;
@@ -300,6 +338,13 @@ extern "C" int gp_bn_fwd_stats(const void* x, int x_dtype, int64_t N, int64_t C,
   const double inv = (N > 0 && HW > 0) ? 1.0 / ((double)N * (double)HW) : 0.0;
   return bn_launch(0, x, x_dtype, nullptr, x_dtype, nullptr, nullptr, GP_F32, N, C, HW, out,
                    out_dtype, workspace, inv, stream);
+}
+
+extern "C" int gp_bn_fwd_mean_var(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW,
+                                  void* out, int out_dtype, void* workspace, void* stream) {
+  const double inv = (N > 0 && HW > 0) ? 1.0 / ((double)N * (double)HW) : 0.0;
+  return bn_launch(0, x, x_dtype, nullptr, x_dtype, nullptr, nullptr, GP_F32, N, C, HW, out,
+                   out_dtype, workspace, inv, stream, 1);
 }
 
 extern "C" int gp_bn_bwd_stats(const void* gy, int gy_dtype, const void* xhat_or_x, int x_dtype,

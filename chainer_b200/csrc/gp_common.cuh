@@ -30,7 +30,8 @@ struct GpTuning {
   int ctas_per_sm;  // persistent grid = SMs * ctas_per_sm
   int persistent;   // 1: balanced contiguous range per CTA; 0: one tile per CTA
   int bn_threads;
-  int pipeline;     // 1: float32 lists use the software-pipelined walker
+  int pipeline;     // (unused: the register-pipelined walker was measured slower and removed)
+  int bn_ctas_per_sm;
 };
 extern GpTuning g_gp_tuning;
 int gp_sm_count_cached();

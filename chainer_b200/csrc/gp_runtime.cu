@@ -29,7 +29,7 @@ int gp_cuda_fail(cudaError_t e, const char* what) {
 
 // defaults: see DESIGN.md "tuning"
 GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 0, /*ctas_per_sm*/ 16, /*persistent*/ 0,
-                        /*bn_threads*/ 256, /*pipeline*/ 1};
+                        /*bn_threads*/ 256, /*pipeline*/ 0, /*bn_ctas_per_sm*/ 4};
 
 gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 0, /*tile*/ 4096, /*stages*/ 4, /*ctas*/ 1, /*debug*/ 0, /*chunk*/ 2048};
 
@@ -61,6 +61,7 @@ int gp_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "persistent")) g_gp_tuning.persistent = value;
   else if (!strcmp(key, "bn_threads")) g_gp_tuning.bn_threads = value;
   else if (!strcmp(key, "pipeline")) g_gp_tuning.pipeline = value;
+  else if (!strcmp(key, "bn_ctas_per_sm")) g_gp_tuning.bn_ctas_per_sm = value < 1 ? 1 : value;
   else if (!strcmp(key, "bulk")) gpb::g_bulk_tuning.enable = value;
   else if (!strcmp(key, "bulk_tile")) gpb::g_bulk_tuning.tile = value < 512 ? 512 : (value & ~511);
   else if (!strcmp(key, "bulk_stages")) gpb::g_bulk_tuning.stages = value < 2 ? 2 : value;
@@ -81,6 +82,7 @@ int gp_get_tuning(const char* key, int* value) {
   else if (!strcmp(key, "persistent")) *value = g_gp_tuning.persistent;
   else if (!strcmp(key, "bn_threads")) *value = g_gp_tuning.bn_threads;
   else if (!strcmp(key, "pipeline")) *value = g_gp_tuning.pipeline;
+  else if (!strcmp(key, "bn_ctas_per_sm")) *value = g_gp_tuning.bn_ctas_per_sm;
   else if (!strcmp(key, "bulk")) *value = gpb::g_bulk_tuning.enable;
   else if (!strcmp(key, "bulk_tile")) *value = gpb::g_bulk_tuning.tile;
   else if (!strcmp(key, "bulk_stages")) *value = gpb::g_bulk_tuning.stages;

@@ -44,6 +44,15 @@ struct SgdOp {
 
   static __device__ __forceinline__ int key(const gp_seg_t& g) { return g.dtype1; }
 
+  // where the (summed) gradient of element e comes from: the packed buffer, or --
+  // stand-alone optimizer.update() without a communicator, buffer == NULL -- the
+  // gradient array itself (then dtype0 == buffer dtype is required by the host)
+  template <class B>
+  __device__ __forceinline__ const B* grad_src(const gp_seg_t& g, int64_t e) const {
+    return buffer ? reinterpret_cast<const B*>(buffer) + g.buf_off + e
+                  : reinterpret_cast<const B*>(g.ptr[0]) + e;
+  }
+
   // one element, arithmetic in P exactly as update_core_cpu
   // (momentum_sgd.py:61-73: v *= momentum; v -= lr * grad; param += v)
   template <class P>
@@ -72,7 +81,7 @@ struct SgdOp {
         r.pp[u] = mptr<P>(seg[u]->ptr[1]) + e[u];
         r.pv[u] = mptr<P>(seg[u]->ptr[2]) + e[u];
         r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
-        r.rb[u] = ld4_stream(reinterpret_cast<const B*>(buffer) + seg[u]->buf_off + e[u]);
+        r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
         r.rp[u] = ld4(r.pp[u]);
         r.rv[u] = ld4(r.pv[u]);
       }
@@ -158,7 +167,7 @@ struct SgdOp {
   template <class B, class P, int SM>
   __device__ __forceinline__ void one(const gp_seg_t& sg, int64_t e) const {
     using CP = typename Carrier<P>::type;
-    const auto xb = to_carrier(reinterpret_cast<const B*>(buffer)[sg.buf_off + e]);
+    const auto xb = to_carrier(*grad_src<B>(sg, e));
     const CP g = gpw::mean_grad_value<B, P, SM>(xb, s);
     P* pp = mptr<P>(sg.ptr[1]) + e;
     P* pv = mptr<P>(sg.ptr[2]) + e;
@@ -191,7 +200,7 @@ extern "C" int gp_unpack_momentum_sgd(const void* buffer, int buf_dtype, const i
   op.lr = lr;
   op.momentum = momentum;
   op.write_grad = write_grad;
-  if (layout_hint && n_segs > 0) {
+  if (layout_hint && n_segs > 0 && buffer) {
     gpb::BulkArgs a = {};
     a.csum = d_csum; a.segs = d_segs; a.n_segs = n_segs; a.begin = elem_begin; a.end = elem_end;
     a.buffer = buffer;

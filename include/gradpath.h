@@ -157,6 +157,11 @@ int gp_unpack_scale(const void* buffer, int buf_dtype, const int64_t* d_csum,
  * per warp, no dtype dispatch) or, when enabled by gp_set_tuning("bulk", 1),
  * the TMA-staged kernel of gp_bulk.cuh.  Results are identical either way.
  *
+ * buffer == NULL (fused update kernels): there is no packed buffer; the gradient
+ * of element k is read from ptr0[k] itself (every dtype0 must equal buf_dtype).
+ * This is `optimizer.update()` without a communicator as ONE multi-tensor launch
+ * (chainer/optimizer.py:857-894: one kernel per parameter in the reference).
+ *
  * gp_unpack_momentum_sgd: fused unpack + descale + MomentumSGD update.
  *   g = (dtype0)((buf_dtype)(scale * buffer[buf_off + k]))
  *   v = momentum * v - lr * g ;  param += v        (arithmetic in dtype1)
@@ -211,6 +216,10 @@ int gp_check_finite(const void* buffer, int dtype, int64_t n_elems, int32_t* d_f
 size_t gp_bn_workspace_bytes(int64_t C);
 int gp_bn_fwd_stats(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW, void* out,
                     int out_dtype, void* workspace, void* stream);
+/* Same pass, single rank: out[0:C] = mean, out[C:2C] = var = sqmean - mean^2
+ * (no allreduce follows, so the finish step is folded into the kernel). */
+int gp_bn_fwd_mean_var(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW, void* out,
+                       int out_dtype, void* workspace, void* stream);
 /*
  * gp_bn_bwd_stats: out[0:C] = sum(gy), out[C:2C] = sum(gy * x_hat) over (N, HW).
  * Replaces `gy.sum(axis)`, `(gy * x_hat).sum(axis)` of

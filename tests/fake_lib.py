@@ -199,7 +199,10 @@ class FakeLib(object):
             _buf_write(int(buffer) + (off + e0) * isz, e1 - e0, buf_dtype, vals)
         return 0
 
-    def _mean_grad(self, buffer, buf_dtype, off, e0, e1, scale, gdt):
+    def _mean_grad(self, buffer, buf_dtype, off, e0, e1, scale, gdt, seg=None, size=None):
+        if not buffer:        # stand-alone update: the gradient array is the source
+            src = _view(int(seg['ptr'][0]), size, _ID2DT[buf_dtype])[e0:e1]
+            return og.scale_buffer(np.array(src), _ID2DT[buf_dtype], scale).astype(gdt)
         isz = 2 if buf_dtype in (6, 9) else (4 if buf_dtype == 7 else 8)
         raw = _buf_read(int(buffer) + (off + e0) * isz, e1 - e0, buf_dtype)
         return og.scale_buffer(np.array(raw), _ID2DT[buf_dtype], scale).astype(gdt)
@@ -222,7 +225,8 @@ class FakeLib(object):
         for j, e0, e1 in self._pieces(csum, n, begin, end):
             pdt = _ID2DT[int(segs['dtype1'][j])]
             size = int(csum[j + 1] - csum[j])
-            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt)
+            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt,
+                                segs[j], size)
             p = _view(int(segs['ptr'][j, 1]), size, pdt)[e0:e1]
             v = _view(int(segs['ptr'][j, 2]), size, pdt)[e0:e1]
             og.momentum_sgd_update(p, g, v, lr, momentum)
@@ -238,7 +242,8 @@ class FakeLib(object):
         for j, e0, e1 in self._pieces(csum, n, begin, end):
             pdt = _ID2DT[int(segs['dtype1'][j])]
             size = int(csum[j + 1] - csum[j])
-            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt)
+            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt,
+                                segs[j], size)
             p = _view(int(segs['ptr'][j, 1]), size, pdt)[e0:e1]
             m = _view(int(segs['ptr'][j, 2]), size, pdt)[e0:e1]
             v = _view(int(segs['ptr'][j, 3]), size, pdt)[e0:e1]
@@ -267,6 +272,10 @@ class FakeLib(object):
         xs = _view(x, N * C * HW, _ID2DT[x_dtype]).reshape(N, C, HW)
         _view(out, 2 * C, _ID2DT[out_dtype])[...] = og.bn_fwd_stats(xs, _ID2DT[out_dtype])
         return 0
+
+    def gp_bn_fwd_mean_var(self, x, x_dtype, N, C, HW, out, out_dtype, ws, stream):
+        self.gp_bn_fwd_stats(x, x_dtype, N, C, HW, out, out_dtype, ws, stream)
+        return self.gp_bn_finish_mean_var(out, out_dtype, C, 1.0, int(out) + C * (2 if out_dtype == 6 else (4 if out_dtype == 7 else 8)), stream)
 
     def gp_bn_bwd_stats(self, gy, gy_dtype, xh, x_dtype, mean, inv_std, stat_dtype, N, C, HW, out,
                         out_dtype, ws, stream):

@@ -287,3 +287,34 @@ def test_double_buffering_optimizer_on_gpu(comm):
     opt.update()
     opt.wait()
     assert actual.t == 1
+
+
+@pytest.mark.parametrize('opt_name', ['momentum_sgd', 'adam'])
+def test_standalone_multi_tensor_update_on_gpu(opt_name):
+    """optimizer.update() without a communicator (buffer == NULL kernels), mixed
+    float16 / float32 parameters, full-size-ish tensors: bit-exact vs the oracle."""
+    import torch
+    from chainer_b200.core.link import link_from_named_arrays
+    rng = np.random.default_rng(21)
+    spec = [('/a/W', (300, 200), np.float32), ('/a/b', (7,), np.float32),
+            ('/b/W', (128, 64), np.float16), ('/b/b', (64,), np.float16),
+            ('/c/W', (100000,), np.float32)]
+    host = [np.asarray(rng.standard_normal(s) * 0.05).astype(dt) for _, s, dt in spec]
+    model = link_from_named_arrays([(n, _t(a)) for (n, _, _), a in zip(spec, host)])
+    opt = chainer_b200.MomentumSGD(lr=0.01) if opt_name == 'momentum_sgd' else chainer_b200.Adam()
+    opt.setup(model)
+    st = [dict(m=np.zeros_like(a), v=np.zeros_like(a)) for a in host]
+    for step in range(1, 4):
+        grads = [np.asarray(rng.standard_normal(a.shape) * (0.5 if a.dtype == np.float16 else 1e-2))
+                 .astype(a.dtype) for a in host]
+        for (_, p), g in zip(sorted(model.namedparams()), grads):
+            p.grad = _t(g)
+        opt.update()
+        torch.cuda.synchronize()
+        for (name, p), q, g, s in zip(sorted(model.namedparams()), host, grads, st):
+            if opt_name == 'momentum_sgd':
+                og.momentum_sgd_update(q, g, s['v'], 0.01, 0.9)
+            else:
+                og.adam_update_gpu(q, g, s['m'], s['v'], step)
+            assert_bits_equal(p.data.cpu().numpy(), q, name)
+            assert p.update_rule.t == step

@@ -484,3 +484,35 @@ def test_bucket_bounds():
     assert comm._bucket_bounds(25557096, 4) == [0, 25557096]   # default: one allreduce
     M.size = 1
     assert comm._bucket_bounds(1000, 4) == [0, 1000]
+
+
+def test_standalone_update_is_one_launch_per_group(fake):
+    """GradientMethod.update() without a communicator: one multi-tensor launch per
+    (dtype, hyperparameter) group instead of one kernel per parameter
+    (chainer/optimizer.py:886-889), same results as the per-parameter rules."""
+    model = ExampleMixedModel()
+    ref = ExampleMixedModel()
+    rng = np.random.default_rng(12)
+    for (_, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+        p.data[...] = rng.standard_normal(p.data.shape).astype(p.data.dtype)
+        q.data[...] = p.data
+    opt = chainer_b200.MomentumSGD(lr=0.1, momentum=0.9)
+    opt.setup(model)
+    model.d.b.update_rule.hyperparam.lr = 0.01           # one extra group
+    vs = {}
+    for step in range(1, 3):
+        for (name, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+            g = (rng.standard_normal(p.data.shape) * 0.1).astype(p.data.dtype)
+            p.grad = g.copy()
+            q.grad = g.copy()
+        fake.calls[:] = []
+        opt.update()
+        launches = [c for c in fake.calls if c[0] == 'gp_unpack_momentum_sgd']
+        assert len(launches) == 3                          # float16, float32, float32 with lr override
+        assert opt.t == step
+        for (name, p), (_, q) in zip(sorted(model.namedparams()), sorted(ref.namedparams())):
+            assert p.update_rule.t == step
+            v = vs.setdefault(name, np.zeros_like(q.data))
+            og.momentum_sgd_update(q.data, q.grad, v, 0.01 if name == '/d/b' else 0.1, 0.9)
+            assert_bits_equal(p.data, q.data, name)
+            assert_bits_equal(p.update_rule.state['v'], v, name)
