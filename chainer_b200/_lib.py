@@ -104,6 +104,8 @@ PROTOTYPES = {
     'gp_nccl_mem_free': (c_int, [c_void_p]),
     'gp_nccl_comm_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p)]),
     'gp_nccl_comm_deregister': (c_int, [c_void_p, c_void_p]),
+    'gp_nccl_comm_window_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p), c_int]),
+    'gp_nccl_comm_window_deregister': (c_int, [c_void_p, c_void_p]),
     'gp_ipc_get_handle': (c_int, [c_void_p, c_char_p]),
     'gp_ipc_open_handle': (c_int, [c_char_p, _P(c_void_p)]),
     'gp_ipc_close_handle': (c_int, [c_void_p]),

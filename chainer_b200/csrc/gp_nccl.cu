@@ -36,6 +36,8 @@ struct NcclApi {
   int (*MemFree)(void*);
   int (*CommRegister)(nccl_comm_t, void*, size_t, void**);
   int (*CommDeregister)(nccl_comm_t, void*);
+  int (*CommWindowRegister)(nccl_comm_t, void*, size_t, void**, int);
+  int (*CommWindowDeregister)(nccl_comm_t, void*);
 };
 NcclApi g_nccl = {};
 
@@ -94,6 +96,8 @@ int gp_nccl_load(const char* path) {
   GP_SYM(MemFree, "ncclMemFree");
   GP_SYM(CommRegister, "ncclCommRegister");
   GP_SYM(CommDeregister, "ncclCommDeregister");
+  GP_SYM(CommWindowRegister, "ncclCommWindowRegister");
+  GP_SYM(CommWindowDeregister, "ncclCommWindowDeregister");
 #undef GP_SYM
   if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) {
     gp_set_error("gp_nccl_load: %s lacks the NCCL 2 core symbols", p);
@@ -196,6 +200,20 @@ int gp_nccl_comm_register(void* comm, void* buffer, size_t nbytes, void** handle
 int gp_nccl_comm_deregister(void* comm, void* handle) {
   GP_NEED(CommDeregister, "ncclCommDeregister");
   return nccl_fail(g_nccl.CommDeregister((nccl_comm_t)comm, handle), "ncclCommDeregister");
+}
+
+// NCCL >= 2.27 symmetric memory: a buffer from ncclMemAlloc registered on every
+// rank as a collective-symmetric window lets ncclAllReduce use its symmetric
+// (NVLS / low-latency) kernels.  flags: 1 = NCCL_WIN_COLL_SYMMETRIC.
+int gp_nccl_comm_window_register(void* comm, void* buffer, size_t nbytes, void** window, int flags) {
+  GP_NEED(CommWindowRegister, "ncclCommWindowRegister");
+  return nccl_fail(g_nccl.CommWindowRegister((nccl_comm_t)comm, buffer, nbytes, window, flags),
+                   "ncclCommWindowRegister");
+}
+int gp_nccl_comm_window_deregister(void* comm, void* window) {
+  GP_NEED(CommWindowDeregister, "ncclCommWindowDeregister");
+  return nccl_fail(g_nccl.CommWindowDeregister((nccl_comm_t)comm, window),
+                   "ncclCommWindowDeregister");
 }
 
 }  // extern "C"

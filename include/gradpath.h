@@ -261,6 +261,9 @@ int gp_nccl_mem_alloc(void** ptr, size_t nbytes);
 int gp_nccl_mem_free(void* ptr);
 int gp_nccl_comm_register(void* comm, void* buffer, size_t nbytes, void** handle);
 int gp_nccl_comm_deregister(void* comm, void* handle);
+/* NCCL >= 2.27 symmetric windows (flags 1 = NCCL_WIN_COLL_SYMMETRIC; collective call) */
+int gp_nccl_comm_window_register(void* comm, void* buffer, size_t nbytes, void** window, int flags);
+int gp_nccl_comm_window_deregister(void* comm, void* window);
 
 /* ------------------------------------------- peer-memory allreduce (NVLink) -- */
 /*

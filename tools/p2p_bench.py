@@ -46,10 +46,26 @@ def main():
             return float(t.item())
 
         us_nccl = timeit(lambda: comm.nccl_comm.allReduce(mem.ptr(), mem.ptr(), n, 7, nccl.NCCL_SUM, 0))
+        # NCCL with a symmetric-registered buffer (ncclMemAlloc + ncclCommWindowRegister)
+        us_sym = None
+        try:
+            import ctypes
+            sp = ctypes.c_void_p()
+            nb = (n * 4 + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+            lib.gp_nccl_mem_alloc(ctypes.byref(sp), nb)
+            win = ctypes.c_void_p()
+            lib.gp_nccl_comm_window_register(comm.nccl_comm.handle, sp.value, nb, ctypes.byref(win), 1)
+            lib.gp_memset_async(sp.value, 0, n * 4, 0)
+            us_sym = timeit(lambda: comm.nccl_comm.allReduce(sp.value, sp.value, n, 7, nccl.NCCL_SUM, 0))
+            lib.gp_nccl_comm_window_deregister(comm.nccl_comm.handle, win.value)
+            lib.gp_nccl_mem_free(sp.value)
+        except Exception as e:
+            if rank == 0:
+                print('   symmetric NCCL experiment failed: %s' % e)
         rows = []
-        for mode in (0, 1):
-            for threads in (256, 512):
-                for ctas in (74, 148, 296, 592):
+        for mode in (1,):
+            for threads in (512,):
+                for ctas in (148, 296):
                     lib.gp_p2p_set_tuning(ctas, threads, mode)
                     us = timeit(lambda: comm._p2p.allreduce(np.float32, 0, n, None))
                     rows.append((us, mode, threads, ctas))
@@ -57,6 +73,8 @@ def main():
             S = n * 4
             f = 2.0 * (world - 1) / world
             print('n=%d (%.1f MB)  NCCL %.1f us  busBW %.0f GB/s' % (n, S / 1e6, us_nccl, S / us_nccl / 1e3 * f))
+            if us_sym is not None:
+                print('   NCCL symmetric window: %.1f us  busBW %.0f GB/s' % (us_sym, S / us_sym / 1e3 * f))
             for us, mode, threads, ctas in sorted(rows)[:6]:
                 print('   p2p mode%d t%d c%d: %.1f us  busBW %.0f GB/s  (x%.2f vs NCCL)' % (
                     mode, threads, ctas, us, S / us / 1e3 * f, us_nccl / us))
