@@ -104,6 +104,16 @@ PROTOTYPES = {
     'gp_nccl_mem_free': (c_int, [c_void_p]),
     'gp_nccl_comm_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p)]),
     'gp_nccl_comm_deregister': (c_int, [c_void_p, c_void_p]),
+    'gp_mc_supported': (c_int, [_P(c_int)]),
+    'gp_mc_create': (c_int, [_P(c_void_p), c_int, c_int, c_size_t]),
+    'gp_mc_export_fd': (c_int, [c_void_p, _P(c_int)]),
+    'gp_mc_import_fd': (c_int, [c_void_p, c_int]),
+    'gp_mc_add_device': (c_int, [c_void_p]),
+    'gp_mc_bind': (c_int, [c_void_p]),
+    'gp_mc_pointers': (c_int, [c_void_p, _P(c_void_p), _P(c_void_p), _P(c_size_t)]),
+    'gp_mc_destroy': (c_int, [c_void_p]),
+    'gp_mc_allreduce': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    'gp_mc_set_tuning': (c_int, [c_int, c_int, c_int]),
     'gp_nccl_comm_window_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p), c_int]),
     'gp_nccl_comm_window_deregister': (c_int, [c_void_p, c_void_p]),
     'gp_ipc_get_handle': (c_int, [c_void_p, c_char_p]),
@@ -127,7 +137,7 @@ PROTOTYPES = {
 KERNEL_FUNCS = frozenset([
     'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
-    'gp_p2p_allreduce', 'gp_p2p_allreduce_small'])
+    'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce'])
 
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes'}

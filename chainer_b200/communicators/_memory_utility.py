@@ -241,10 +241,14 @@ class DeviceMemory(object):
         self.size = 0
         self.memory = None
         self._alloc = None
+        # optional callable(nbytes) -> object with .ptr (or None: use cudaMalloc);
+        # the communicator installs the multicast allocator here
+        self.allocator = None
 
     def assign(self, size):
         if size > self.size:
-            self._alloc = _dev._Allocation(size)
+            alloc = self.allocator(size) if self.allocator is not None else None
+            self._alloc = alloc if alloc is not None else _dev._Allocation(size)
             self.memory = _dev._MemPtr(self._alloc.ptr, self._alloc)
             self.size = size
 

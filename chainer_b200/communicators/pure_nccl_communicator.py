@@ -110,6 +110,10 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self.p2p_chunk_bytes = 0         # peer-memory path: pipeline chunk (0: one kernel; measured best)
         self.p2p_max_bytes = 256 << 20   # beyond this NCCL (NVLS) is faster on 4/8 GPUs (measured)
         self._p2p = None
+        # NVSwitch-multicast allreduce (csrc/gp_mc.cu).  None: 4 and 8 ranks when the
+        # devices support it (or as CHAINER_B200_MULTICAST says); True/False: forced
+        self.use_multicast = None
+        self.mc_max_bytes = 0            # 0: no limit
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -154,10 +158,30 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             p2p, good = None, False
         if all(self.mpi_comm.allgather(good)):
             self._p2p = p2p
+            want_mc = self.use_multicast
+            if want_mc is None:
+                env = _p2p.multicast_enabled_by_env()
+                want_mc = (self.size >= 4) if env is None else env not in ('0', '', 'false', 'False')
+            if all(self.mpi_comm.allgather(bool(want_mc) and p2p.multicast_supported)):
+                # the packed buffer becomes a multicast-bound allocation (collective)
+                self.gpu_buffer_a.allocator = self._mc_allocate
         else:
             if p2p is not None:
                 p2p._close(p2p._flag_maps)
             self._p2p = None
+
+    def _mc_allocate(self, nbytes):
+        if self._p2p is None or not self._p2p.multicast_supported:
+            return None
+        alloc = self._p2p.mc_allocate(nbytes)
+        if alloc is None:
+            warnings.warn('NVSwitch multicast unavailable, using the peer-memory kernel: {}'
+                          .format(self._p2p.multicast_error))
+        return alloc
+
+    def _mc_active(self, buf):
+        from chainer_b200.communicators import _p2p
+        return self._p2p is not None and isinstance(buf._alloc, _p2p._McAllocation)
 
     def set_config(self, name, value=True, **kwargs):
         if name == 'allreduce_grad_dtype':
@@ -297,7 +321,18 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
             consume(0, n)
             return
-        if self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
+        if self._mc_active(buf):
+            if itemsize <= 4 and (self.mc_max_bytes <= 0 or n * itemsize <= self.mc_max_bytes):
+                # ONE kernel per rank: the switch reduces (multimem.ld_reduce) and
+                # replicates (multimem.st) this rank's 1/N shard; barriers inside
+                _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+                self._p2p.mc_allreduce(dtype, 0, n, stream)
+                if debug:
+                    self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
+                consume(0, n)
+                return
+            # float64 or over the limit: NCCL below (works on any device pointer)
+        elif self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
             # ONE kernel per rank and chunk reduces over NVLink peer memory (the
             # cross-GPU barriers are inside it).  The chunks are pipelined: the
             # NVLink-bound reduction of chunk i runs on a side stream, on a few

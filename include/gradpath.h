@@ -305,6 +305,36 @@ int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elem
                            double scale, void* stream);
 
 /* ---------------------------------------------------------------- tuning -- */
+/* ---------------------------------------------------------------------------
+ * NVSwitch-multicast (NVLS) allreduce of the packed buffer, 4 / 8 ranks on one box
+ * (csrc/gp_mc.cu).  Replaces nccl_comm.allReduce of
+ * chainermn/communicators/pure_nccl_communicator.py:180-182: rank r reduces its
+ * 1/N shard with multimem.ld_reduce (the switch adds the N copies) and
+ * broadcasts it with multimem.st, both barriers inside the one kernel (the flag
+ * words of the gp_p2p communicator).  float32 / float16 / bfloat16 (16-bit types
+ * accumulate in fp32); summation order is the switch's: parity to rounding.
+ *
+ * Set-up is collective and staged (the host code synchronises between stages):
+ *   gp_mc_create on every rank (rank 0 creates the multicast object)
+ *   rank 0: gp_mc_export_fd -> POSIX fd, passed to the peers (SCM_RIGHTS)
+ *   ranks != 0: gp_mc_import_fd
+ *   gp_mc_add_device on every rank;            -- barrier --
+ *   gp_mc_bind on every rank (cuMemCreate + cuMulticastBindMem + 2 mappings)
+ *                                              -- barrier --
+ *   gp_mc_pointers: the unicast address IS the packed buffer (gpu_buffer_a).
+ */
+int gp_mc_supported(int* supported);
+int gp_mc_create(void** mc, int rank, int n_ranks, size_t nbytes);
+int gp_mc_export_fd(void* mc, int* fd);
+int gp_mc_import_fd(void* mc, int fd);
+int gp_mc_add_device(void* mc);
+int gp_mc_bind(void* mc);
+int gp_mc_pointers(void* mc, void** unicast, void** multicast, size_t* nbytes);
+int gp_mc_destroy(void* mc);
+int gp_mc_allreduce(void* p2p_comm, void* mc, int dtype, int64_t offset_elems, int64_t n_elems,
+                    void* stream);
+int gp_mc_set_tuning(int ctas, int threads, int unroll);
+
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking
  * sweeps; defaults are the tuned values recorded in DESIGN.md. */
 int gp_set_tuning(const char* key, int value);

@@ -59,6 +59,47 @@ def main():
                 got = out.float().cpu().numpy() if dt_name == 'bfloat16' else out.cpu().numpy()
                 assert np.array_equal(got.view(np.uint8), np.asarray(want).view(np.uint8)), \
                     ('p2p allreduce', dt_name, n)
+        # ---- NVSwitch-multicast allreduce kernel (csrc/gp_mc.cu) vs the oracle ----
+        if os.environ.get('CHAINER_B200_MULTICAST') == '1':
+            p2p = comm._p2p
+            if not p2p.multicast_supported:
+                print('MULTICAST UNSUPPORTED: device attribute', flush=True)
+            else:
+                alloc = p2p.mc_allocate(3000000 * 4)
+                if alloc is None:
+                    print('MULTICAST UNSUPPORTED: %s' % p2p.multicast_error, flush=True)
+                else:
+                    for dt_name, tdt, odt in (('float32', torch.float32, np.float32),
+                                              ('float16', torch.float16, np.float16),
+                                              ('bfloat16', torch.bfloat16, og.BF16)):
+                        isz = 4 if dt_name == 'float32' else 2
+                        for n in (1, 7, 4096, 100003, 3000000):
+                            parts = [og.cast(np.random.default_rng(50 + r).standard_normal(n) * (r + 1), odt)
+                                     for r in range(world)]
+                            mine = t(parts[rank]).to(tdt)
+                            lib.gp_memcpy_async(alloc.ptr, mine.data_ptr(), n * isz, 2, 0)
+                            p2p.mc_allreduce(odt, 0, n, None)
+                            out = torch.empty(n, dtype=tdt, device='cuda')
+                            lib.gp_memcpy_async(out.data_ptr(), alloc.ptr, n * isz, 2, 0)
+                            torch.cuda.synchronize()
+                            want = np.asarray(og.allreduce_sum(parts, odt)).astype(np.float64)
+                            got = out.double().cpu().numpy()
+                            mag = np.sum([np.abs(np.asarray(q, dtype=np.float64)) for q in parts], axis=0)
+                            if dt_name == 'float32' and world == 2:
+                                assert np.array_equal(got, want), ('mc allreduce', dt_name, n)
+                            else:
+                                # the switch's order of addition is not the oracle's rank
+                                # order; 16-bit buffers accumulate in fp32 (one rounding)
+                                eps = 2e-7 if dt_name == 'float32' else (1e-3 if dt_name == 'float16' else 8e-3)
+                                assert np.all(np.abs(got - want) <= eps * world * mag + 1e-30), \
+                                    ('mc allreduce', dt_name, n, float(np.max(np.abs(got - want))))
+                            # every rank holds the same bits
+                            mx = out.clone().view(torch.uint8).to(torch.int32).cpu()
+                            mn = mx.clone()
+                            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+                            assert bool((mx == mn).all()), ('mc allreduce replicas differ', dt_name, n)
+                    print('MULTICAST KERNEL OK', flush=True)
         # one-shot small allreduce (MNBN statistics messages): bit-exact, incl. var
         for C in (1, 3, 64, 257, 2048, 4096):
             vals = [np.random.default_rng(90 + r).standard_normal(2 * C).astype(np.float32)
@@ -164,7 +205,8 @@ def main():
                 else:
                     og.adam_update_gpu(q, g, s['m'], s['v'], step)
                 got = p.data.cpu().numpy()
-                if adt is None and (world == 2 or comm._p2p is not None):
+                if adt is None and (world == 2 or (comm._p2p is not None
+                                                   and not comm._mc_active(comm.gpu_buffer_a))):
                     # 2-term sums are order-free; the peer-memory kernel adds in rank
                     # order like the oracle: bit-exact for every world size
                     assert np.array_equal(got, q), (opt_name, name, step)
@@ -224,6 +266,10 @@ def main():
                                    rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(bn.avg_var.cpu().numpy(), z['mn|%d|avg_var' % rank],
                                    rtol=1e-4, atol=1e-6)
+    if os.environ.get('CHAINER_B200_MULTICAST') == '1' and comm._p2p is not None \
+            and comm._p2p.multicast_supported:
+        assert comm._mc_active(comm.gpu_buffer_a), 'the public API should have used the multicast path'
+        print('MULTICAST PATH OK', flush=True)
     comm.finalize()
     print('GPU RANK %d OK' % rank, flush=True)
 

@@ -26,13 +26,14 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize('p2p', ['1', '0'], ids=['peer-memory', 'nccl'])
+@pytest.mark.parametrize('transport', ['peer-memory', 'nccl', 'multicast'])
 @pytest.mark.parametrize('world_size', [2, 4, 8])
-def test_multi_gpu_path(world_size, p2p):
+def test_multi_gpu_path(world_size, transport):
     if _n_gpus() < world_size:
         pytest.skip('needs {} GPUs'.format(world_size))
     env = dict(os.environ)
-    env['CHAINER_B200_P2P'] = p2p
+    env['CHAINER_B200_P2P'] = '0' if transport == 'nccl' else '1'
+    env['CHAINER_B200_MULTICAST'] = '1' if transport == 'multicast' else '0'
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node', str(world_size), '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', '_dist_gpu_worker.py')]
@@ -44,3 +45,7 @@ def test_multi_gpu_path(world_size, p2p):
     for line in out.stdout.splitlines():
         if line.startswith('MNBN statistics exchange'):
             print(line)
+    if transport == 'multicast':
+        if 'MULTICAST UNSUPPORTED' in out.stdout:
+            pytest.skip([ln for ln in out.stdout.splitlines() if 'MULTICAST UNSUPPORTED' in ln][0])
+        assert 'MULTICAST KERNEL OK' in out.stdout and 'MULTICAST PATH OK' in out.stdout

@@ -49,6 +49,8 @@ def main():
         # NCCL with a symmetric-registered buffer (ncclMemAlloc + ncclCommWindowRegister)
         us_sym = None
         try:
+            if os.environ.get('P2P_NCCL_SYMMETRIC') != '1':
+                raise RuntimeError('skipped (set P2P_NCCL_SYMMETRIC=1)')
             import ctypes
             sp = ctypes.c_void_p()
             nb = (n * 4 + (2 << 20) - 1) // (2 << 20) * (2 << 20)
@@ -69,9 +71,33 @@ def main():
                     lib.gp_p2p_set_tuning(ctas, threads, mode)
                     us = timeit(lambda: comm._p2p.allreduce(np.float32, 0, n, None))
                     rows.append((us, mode, threads, ctas))
+        mc_rows = []
+        if comm._p2p.multicast_supported and os.environ.get('P2P_MULTICAST', '1') == '1':
+            alloc = comm._p2p.mc_allocate(n * 4)
+            if alloc is None:
+                if rank == 0:
+                    print('   multicast unavailable: %s' % comm._p2p.multicast_error)
+            else:
+                for dt, dname in ((np.float32, 'f32'), (np.float16, 'f16')):
+                    ne = n if dt is np.float32 else 2 * n
+                    for threads in (256, 512):
+                        for ctas in (32, 74, 148, 296):
+                            for unroll in (2, 4, 8):
+                                if dname == 'f16' and (threads, unroll) != (512, 4):
+                                    continue
+                                lib.gp_mc_set_tuning(ctas, threads, unroll)
+                                us = timeit(lambda: comm._p2p.mc_allreduce(dt, 0, ne, None))
+                                mc_rows.append((dname, us, threads, ctas, unroll))
+                lib.gp_mc_set_tuning(0, 512, 4)
+                comm._p2p.mc_release()
         if rank == 0:
             S = n * 4
             f = 2.0 * (world - 1) / world
+            for dname in ('f32', 'f16'):
+                sel = sorted(r for r in mc_rows if r[0] == dname)
+                for _, us, threads, ctas, unroll in sel[:4] + sel[-1:]:
+                    print('   multicast %s t%d c%d u%d: %.1f us  busBW %.0f GB/s  (x%.2f vs NCCL f32)' % (
+                        dname, threads, ctas, unroll, us, S / us / 1e3 * f, us_nccl / us))
             print('n=%d (%.1f MB)  NCCL %.1f us  busBW %.0f GB/s' % (n, S / 1e6, us_nccl, S / us_nccl / 1e3 * f))
             if us_sym is not None:
                 print('   NCCL symmetric window: %.1f us  busBW %.0f GB/s' % (us_sym, S / us_sym / 1e3 * f))
