@@ -44,6 +44,8 @@ def parse_args():
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
     ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
+    ap.add_argument('--multicast', choices=['auto', 'on', 'off'], default='auto',
+                    help='NVSwitch multicast allreduce kernel (auto: 4 and 8 GPUs)')
     ap.add_argument('--p2p-chunk-mb', type=float, default=None)
     ap.add_argument('--p2p-ctas', type=int, default=None)
     ap.add_argument('--cpu-seconds', type=float, default=10.0,
@@ -244,6 +246,8 @@ def b200_main(args):
     comm.write_grad = write_grad
     if args.no_p2p:
         comm.use_p2p = False
+    if args.multicast != 'auto':
+        comm.use_multicast = args.multicast == 'on'
     if args.p2p_chunk_mb is not None:
         comm.p2p_chunk_bytes = int(args.p2p_chunk_mb * (1 << 20))
     if args.p2p_ctas is not None:
@@ -366,8 +370,7 @@ def b200_main(args):
                                 n_sets),
             'api': 'create_multi_node_optimizer(MomentumSGD|Adam, pure_nccl).update()',
             'bucket_bytes': comm.bucket_bytes if world > 1 else None,
-            'allreduce_impl': (None if world == 1 else
-                               ('peer-memory kernel (gp_p2p)' if comm._p2p is not None else 'nccl')),
+            'allreduce_impl': (None if world == 1 else _allreduce_impl(comm)),
         },
         'roofline': {
             'bound': 'hbm', 'kernel': kern['update_kernel'], 'achieved': achieved, 'peak': peak,
@@ -435,6 +438,14 @@ def time_kernels(torch, lib, comm, model, actual, opt, set_grads, optimizer_name
             'launches_per_step': per_step}
 
 
+def _allreduce_impl(comm):
+    if comm._p2p is None:
+        return 'nccl'
+    if comm._mc_active(comm.gpu_buffer_a):
+        return 'nvswitch multicast kernel (gp_mc)'
+    return 'peer-memory kernel (gp_p2p)'
+
+
 def time_allreduce(torch, dist, comm, n, bsz, world):
     """NCCL-tests convention: algBW = S / t, busBW = algBW * 2(N-1)/N."""
     from chainer_b200 import nccl
@@ -442,7 +453,10 @@ def time_allreduce(torch, dist, comm, n, bsz, world):
     buf = comm.gpu_buffer_a
     type_id = 7 if bsz == 4 else 6
     dt = np.float32 if bsz == 4 else np.float16
-    if comm._p2p is not None:
+    if comm._p2p is not None and comm._mc_active(buf):
+        def one():
+            comm._p2p.mc_allreduce(dt, 0, n, None)
+    elif comm._p2p is not None:
         def one():
             comm._p2p.allreduce(dt, 0, n, None)
     else:
@@ -466,7 +480,7 @@ def time_allreduce(torch, dist, comm, n, bsz, world):
     S = n * bsz
     alg = S / us / 1e3
     busbw = alg * 2 * (world - 1) / world
-    return {'impl': 'peer-memory kernel' if comm._p2p is not None else 'nccl',
+    return {'impl': _allreduce_impl(comm),
             'bytes': S, 'us': us, 'alg_gbs': alg, 'bus_gbs': busbw,
             'frac_of_900': busbw / 900.0, 'frac_of_measured_725': busbw / 725.0}
 

@@ -82,7 +82,7 @@ def main():
                     ne = n if dt is np.float32 else 2 * n
                     for threads in (256, 512):
                         for ctas in (32, 74, 148, 296):
-                            for unroll in (2, 4, 8):
+                            for unroll in (4, 8):
                                 if dname == 'f16' and (threads, unroll) != (512, 4):
                                     continue
                                 lib.gp_mc_set_tuning(ctas, threads, unroll)
