@@ -44,6 +44,7 @@ def parse_args():
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
     ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
+    ap.add_argument('--mc-chunk-mb', type=float, default=None, help='multicast path: pipeline chunk size')
     ap.add_argument('--multicast', choices=['auto', 'on', 'off'], default='auto',
                     help='NVSwitch multicast allreduce kernel (auto: 4 and 8 GPUs)')
     ap.add_argument('--p2p-chunk-mb', type=float, default=None)
@@ -248,6 +249,8 @@ def b200_main(args):
         comm.use_p2p = False
     if args.multicast != 'auto':
         comm.use_multicast = args.multicast == 'on'
+    if args.mc_chunk_mb is not None:
+        comm.mc_chunk_bytes = int(args.mc_chunk_mb * (1 << 20))
     if args.p2p_chunk_mb is not None:
         comm.p2p_chunk_bytes = int(args.p2p_chunk_mb * (1 << 20))
     if args.p2p_ctas is not None:

@@ -114,6 +114,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         # devices support it (or as CHAINER_B200_MULTICAST says); True/False: forced
         self.use_multicast = None
         self.mc_max_bytes = 0            # 0: no limit
+        self.mc_chunk_bytes = 0          # multicast path: pipeline chunk (0: one kernel)
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -321,30 +322,30 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
             consume(0, n)
             return
+        reduce_range = None
         if self._mc_active(buf):
             if itemsize <= 4 and (self.mc_max_bytes <= 0 or n * itemsize <= self.mc_max_bytes):
                 # ONE kernel per rank: the switch reduces (multimem.ld_reduce) and
                 # replicates (multimem.st) this rank's 1/N shard; barriers inside
-                _memory_utility._batched_pack_params(pd, buf, dtype, stream)
-                self._p2p.mc_allreduce(dtype, 0, n, stream)
-                if debug:
-                    self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
-                consume(0, n)
-                return
+                reduce_range = self._p2p.mc_allreduce
+                chunk_bytes = self.mc_chunk_bytes
             # float64 or over the limit: NCCL below (works on any device pointer)
         elif self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
-            # ONE kernel per rank and chunk reduces over NVLink peer memory (the
-            # cross-GPU barriers are inside it).  The chunks are pipelined: the
-            # NVLink-bound reduction of chunk i runs on a side stream, on a few
-            # CTAs, under the HBM-bound pack of chunk i+1 and update of chunk i-1.
+            # ONE kernel per rank reduces over NVLink peer memory (the cross-GPU
+            # barriers are inside it)
             self._p2p.ensure(buf, stream)
-            per = max(self.p2p_chunk_bytes // itemsize, 4096) // 4096 * 4096
-            cb = list(range(0, n, per)) + [n] if self.p2p_chunk_bytes > 0 else [0, n]
+            reduce_range = self._p2p.allreduce
+            chunk_bytes = self.p2p_chunk_bytes
+        if reduce_range is not None:
+            # Optional chunking: the NVLink-bound reduction of chunk i runs on a side
+            # stream under the HBM-bound pack of chunk i+1 and update of chunk i-1.
+            per = max(chunk_bytes // itemsize, 4096) // 4096 * 4096
+            cb = list(range(0, n, per)) + [n] if chunk_bytes > 0 else [0, n]
             if len(cb) > 2 and cb[-1] - cb[-2] < per // 2:
                 del cb[-2]
             if len(cb) == 2:
                 _memory_utility._batched_pack_params(pd, buf, dtype, stream)
-                self._p2p.allreduce(dtype, 0, n, stream)
+                reduce_range(dtype, 0, n, stream)
                 if debug:
                     self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
                 consume(0, n)
@@ -359,7 +360,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 ev = self._event(2 * b)
                 ev.record(stream)
                 cs.wait_event(ev)
-                self._p2p.allreduce(dtype, lo, hi - lo, cs)
+                reduce_range(dtype, lo, hi - lo, cs)
                 self._event(2 * b + 1).record(cs)
             for b in range(len(cb) - 1):
                 stream.wait_event(self._event(2 * b + 1))

@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(512) mc_allreduce_kernel(const McArgs a) {
   finish_all(a.p);
 }
 
-int g_mc_ctas = 0;
-int g_mc_threads = 512;
+// few, small CTAs keep the switch's reduction pipeline fed without over-subscribing
+// it (tools/p2p_bench.py at N = 8: 32 x 256 threads 241 us, 296 x 512 304 us)
+int g_mc_ctas = 32;
+int g_mc_threads = 256;
 int g_mc_unroll = 4;
 
 template <class T>
