@@ -114,7 +114,9 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         # devices support it (or as CHAINER_B200_MULTICAST says); True/False: forced
         self.use_multicast = None
         self.mc_max_bytes = 0            # 0: no limit
-        self.mc_chunk_bytes = 0          # multicast path: pipeline chunk (0: one kernel)
+        # multicast path: pipeline chunk (0: one kernel; None: two chunks from 32 MB
+        # up -- measured best at N = 4 and 8, profiles/r01_bench_n{4,8}_mc*.json)
+        self.mc_chunk_bytes = None
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -329,6 +331,9 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 # replicates (multimem.st) this rank's 1/N shard; barriers inside
                 reduce_range = self._p2p.mc_allreduce
                 chunk_bytes = self.mc_chunk_bytes
+                if chunk_bytes is None:
+                    half = ((n + 1) // 2 + 4095) // 4096 * 4096
+                    chunk_bytes = half * itemsize if n * itemsize >= (32 << 20) else 0
             # float64 or over the limit: NCCL below (works on any device pointer)
         elif self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
             # ONE kernel per rank reduces over NVLink peer memory (the cross-GPU
