@@ -10,6 +10,7 @@ reached through ctypes (``chainer_b200._lib``).  There is no CPU fallback.
 __version__ = '0.1.0'
 
 from chainer_b200 import config  # NOQA
+from chainer_b200 import optimizer_hooks  # NOQA
 from chainer_b200.communicators import CommunicatorBase  # NOQA
 from chainer_b200.communicators import create_communicator  # NOQA
 from chainer_b200.optimizers import create_multi_node_optimizer  # NOQA

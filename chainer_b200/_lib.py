@@ -41,6 +41,14 @@ SEG_DTYPE = np.dtype([
 ])
 assert SEG_DTYPE.itemsize == 64
 
+
+
+class GpHooks(ctypes.Structure):
+    """ctypes mirror of ``gp_hooks_t`` (include/gradpath.h)."""
+    _fields_ = [('clip_rate', ctypes.c_void_p), ('weight_decay', ctypes.c_double),
+                ('loss_scale', ctypes.c_double)]
+
+
 _P = ctypes.POINTER
 # name -> (restype, argtypes); one entry per declaration of include/gradpath.h
 PROTOTYPES = {
@@ -104,6 +112,19 @@ PROTOTYPES = {
     'gp_nccl_mem_free': (c_int, [c_void_p]),
     'gp_nccl_comm_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p)]),
     'gp_nccl_comm_deregister': (c_int, [c_void_p, c_void_p]),
+    'gp_unpack_momentum_sgd_hooked': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                              c_double, c_double, c_double, c_int, c_int,
+                                              c_void_p, c_void_p]),
+    'gp_unpack_adam_hooked': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                      c_double, c_double, c_double, c_double, c_double, c_double,
+                                      c_double, c_double, c_double, c_int, c_int, c_int,
+                                      c_void_p, c_void_p]),
+    'gp_sqnorm_workspace_bytes': (c_size_t, []),
+    'gp_sqnorm': (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_double, c_void_p, c_void_p,
+                          c_void_p]),
+    'gp_scale_by_device': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    'gp_weight_decay': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_double, c_void_p]),
+    'gp_divide': (c_int, [c_void_p, c_int, c_int64, c_double, c_void_p]),
     'gp_mc_supported': (c_int, [_P(c_int)]),
     'gp_mc_create': (c_int, [_P(c_void_p), c_int, c_int, c_size_t]),
     'gp_mc_export_fd': (c_int, [c_void_p, _P(c_int)]),
@@ -137,10 +158,13 @@ PROTOTYPES = {
 KERNEL_FUNCS = frozenset([
     'gp_pack', 'gp_unpack_scale', 'gp_unpack_momentum_sgd', 'gp_unpack_adam', 'gp_scale',
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
-    'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce'])
+    'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce',
+    'gp_unpack_momentum_sgd_hooked', 'gp_unpack_adam_hooked', 'gp_sqnorm', 'gp_scale_by_device',
+    'gp_weight_decay', 'gp_divide'])
 
 # functions whose int return value is an error code
-_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes'}
+_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',
+             'gp_sqnorm_workspace_bytes'}
 
 
 class GradpathError(RuntimeError):

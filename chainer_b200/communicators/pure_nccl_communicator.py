@@ -293,6 +293,26 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             del bounds[-2]                       # fold a small tail into the last bucket
         return bounds
 
+    @staticmethod
+    def _auto_mc_chunk_bytes(n_elems, itemsize):
+        """Two chunks from 32 MB up, one kernel below (measured: profiles/r01_bench_n*_mc*)."""
+        if n_elems * itemsize < (32 << 20):
+            return 0
+        half = ((n_elems + 1) // 2 + 4095) // 4096 * 4096
+        return half * itemsize
+
+    @staticmethod
+    def _chunk_bounds(n_elems, itemsize, chunk_bytes):
+        """Element bounds of the pipeline chunks: multiples of 4096 elements (16-byte
+        vectors for every dtype, whole walker tiles), a short tail folded in."""
+        if chunk_bytes <= 0:
+            return [0, n_elems]
+        per = max(chunk_bytes // itemsize, 4096) // 4096 * 4096
+        cb = list(range(0, n_elems, per)) + [n_elems]
+        if len(cb) > 2 and cb[-1] - cb[-2] < per // 2:
+            del cb[-2]
+        return cb
+
     def _event(self, i):
         while len(self._events) <= i:
             self._events.append(_dev.Event())
@@ -332,8 +352,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
                 reduce_range = self._p2p.mc_allreduce
                 chunk_bytes = self.mc_chunk_bytes
                 if chunk_bytes is None:
-                    half = ((n + 1) // 2 + 4095) // 4096 * 4096
-                    chunk_bytes = half * itemsize if n * itemsize >= (32 << 20) else 0
+                    chunk_bytes = self._auto_mc_chunk_bytes(n, itemsize)
             # float64 or over the limit: NCCL below (works on any device pointer)
         elif self._p2p is not None and (self.size == 2 or n * itemsize <= self.p2p_max_bytes):
             # ONE kernel per rank reduces over NVLink peer memory (the cross-GPU
@@ -344,10 +363,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         if reduce_range is not None:
             # Optional chunking: the NVLink-bound reduction of chunk i runs on a side
             # stream under the HBM-bound pack of chunk i+1 and update of chunk i-1.
-            per = max(chunk_bytes // itemsize, 4096) // 4096 * 4096
-            cb = list(range(0, n, per)) + [n] if chunk_bytes > 0 else [0, n]
-            if len(cb) > 2 and cb[-1] - cb[-2] < per // 2:
-                del cb[-2]
+            cb = self._chunk_bounds(n, itemsize, chunk_bytes)
             if len(cb) == 2:
                 _memory_utility._batched_pack_params(pd, buf, dtype, stream)
                 reduce_range(dtype, 0, n, stream)
@@ -462,8 +478,7 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             self._fused_plan = plan if (plan is not None and plan.cacheable) else None
             if plan is None:
                 return False
-        plan.run(stream if stream is not None else _dev.Stream.null)
-        return True
+        return plan.run(stream if stream is not None else _dev.Stream.null)
 
     def invalidate_plans(self):
         """Drop cached plans (call after replacing parameter or state arrays
@@ -492,6 +507,8 @@ class _FusedPlan(object):
         self.optimizer = optimizer
         self.zero_fill = zero_fill
         self.params, self.others = fp
+        self.clip_hook, self.wd_hook = _fusable_hooks(optimizer)
+        self.hook_struct = _lib.GpHooks()
         self.rules = [p.update_rule for p in self.params]
         self.other_rules = [p.update_rule for p in self.others
                             if p.update_rule is not None and p.update_rule.enabled]
@@ -537,6 +554,11 @@ class _FusedPlan(object):
                     buf_offsets=self.pd.host_csum[idx])
                 self.groups.append((self.rules[idx[0]], idx, sub))
         return self
+
+    def has_param_loss_scale(self):
+        # backward(loss_scale=...) marks every parameter; looking at one is enough to
+        # notice loss scaling driven from outside the optimizer object
+        return bool(self.params) and getattr(self.params[0], '_loss_scale', None) is not None
 
     def matches(self, model, optimizer, zero_fill):
         return (model is self.model and optimizer is self.optimizer and
@@ -588,9 +610,19 @@ class _FusedPlan(object):
         return ent
 
     def run(self, stream):
+        """One fused step; False (nothing done) when this step must run unfused."""
         comm = self.comm
         comm._init_comms()
         dtype = comm._allreduce_dtype()
+        # optimizer hooks and loss scaling of this step (chainer/optimizer.py:881-883,
+        # 286-291): the loss scale is what backward() left on the parameters
+        clip, wdh = self.clip_hook, self.wd_hook
+        loss_scale = None
+        if self.optimizer._loss_scale is not None or self.has_param_loss_scale():
+            scales = set(getattr(p, '_loss_scale', None) for p in self.params)
+            if len(scales) != 1:
+                return False              # per-parameter loss scales: the unfused sequence
+            loss_scale = scales.pop()
         try:
             tables = self._tables(stream)
         except _PlanStale:
@@ -598,7 +630,7 @@ class _FusedPlan(object):
             if not comm.multi_node_mean_grad_and_update(self.model, self.optimizer,
                                                         self.zero_fill, stream):
                 raise ValueError('gradient dtype does not match its parameter')
-            return
+            return True
         # t bookkeeping of GradientMethod.update / UpdateRule.update
         # (chainer/optimizer.py:857-894, 236-250)
         self.optimizer.t += 1
@@ -612,13 +644,24 @@ class _FusedPlan(object):
         if stream != _dev.Stream.null and needs_sync:
             _dev.Stream.null.synchronize()
         if n_elems == 0:
-            return
+            return True
         lib = _lib.get()
         buf_id = _dev.dtype_id(dtype)
         scale = 1.0 / comm.size
         wg = 1 if comm.write_grad else 0
         buf_ptr = comm.gpu_buffer_a.ptr()
         sp = stream.ptr
+        hooked = clip is not None or wdh is not None or loss_scale is not None
+        hk_addr = None
+        if hooked:
+            hk = self.hook_struct
+            decay = 0.0
+            if wdh is not None:
+                decay = float(wdh.rate) * (loss_scale if loss_scale is not None else 1.0)
+            hk.weight_decay = decay
+            hk.loss_scale = float(loss_scale) if loss_scale is not None else 0.0
+            hk.clip_rate = clip.scratch().rate_ptr if clip is not None else None
+            hk_addr = ctypes.addressof(hk)
         launches = []
         for rep, idx, t in tables.groups:
             key = rep.fused_key()                 # re-read hyperparameters (and alpha_t)
@@ -630,14 +673,34 @@ class _FusedPlan(object):
         def launch(key, t, begin, end):
             hint = t.layout_hint(dtype)
             if key[0] == 'momentum_sgd':
-                lib.gp_unpack_momentum_sgd(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
-                                           begin, end, scale, key[1], key[2], wg, hint, sp)
+                if hooked:
+                    lib.gp_unpack_momentum_sgd_hooked(buf_ptr, buf_id, t.d_csum, t.d_segs,
+                                                      t.n_params, begin, end, scale, key[1],
+                                                      key[2], wg, hint, hk_addr, sp)
+                else:
+                    lib.gp_unpack_momentum_sgd(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
+                                               begin, end, scale, key[1], key[2], wg, hint, sp)
+            elif hooked:
+                lib.gp_unpack_adam_hooked(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin,
+                                          end, scale, key[1], key[2], key[3], key[4], key[5],
+                                          key[6], key[7], key[8], key[9], wg, hint, hk_addr, sp)
             else:
                 lib.gp_unpack_adam(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin, end,
                                    scale, key[1], key[2], key[3], key[4], key[5], key[6], key[7],
                                    key[8], key[9], wg, hint, sp)
 
-        if len(launches) == 1:
+        if clip is not None:
+            # the global norm needs every bucket reduced: one reduction over the whole
+            # allreduced buffer forms the rate on the device, then the update(s) run
+            threshold = float(clip.threshold)
+            sc = clip.scratch()
+
+            def consume(begin, end):
+                if end == n_elems:
+                    lib.gp_sqnorm(buf_ptr, buf_id, n_elems, scale, 0, threshold, sc.ws, sc.out, sp)
+                    for key, t in launches:
+                        launch(key, t, 0, t.n_elems)
+        elif len(launches) == 1:
             key0, t0 = launches[0]
 
             def consume(begin, end):
@@ -650,6 +713,7 @@ class _FusedPlan(object):
                     for key, t in launches:
                         launch(key, t, 0, t.n_elems)
         comm._pipeline(pd, dtype, stream, consume)
+        return True
 
 
 class _PlanStale(Exception):
@@ -678,15 +742,34 @@ class _TableSet(object):
                 sub.set_ptr0(ptrs[idx], stream)
 
 
+def _fusable_hooks(optimizer):
+    """The optimizer-level hooks as (GradientClipping or None, WeightDecay or None) when
+    the fused kernels can apply them in registration order -- no hooks,
+    [WeightDecay], [GradientClipping], [GradientClipping, WeightDecay] -- else None
+    (other orders, other hooks, 'post' hooks: the reference sequence runs unfused)."""
+    from chainer_b200 import optimizer_hooks as H
+    hookable = getattr(optimizer, '_hookable', None)
+    if hookable is None or hookable._post:
+        return None
+    pre = list(hookable._pre.values())
+    kinds = [type(h) for h in pre]
+    if not kinds:
+        return (None, None)
+    if kinds == [H.WeightDecay]:
+        return (None, pre[0])
+    if kinds == [H.GradientClipping]:
+        return (pre[0], None)
+    if kinds == [H.GradientClipping, H.WeightDecay]:
+        return (pre[0], pre[1])
+    return None
+
+
 def _fusion_plan(model, optimizer, zero_fill):
     """Decide whether ``optimizer.update(None)`` can be fused; returns
     (params_in_layout_order, other_params) or None."""
-    if getattr(optimizer, '_loss_scale', None) is not None:
-        return None
     if getattr(optimizer, '_loss_scaling_is_dynamic', False):
-        return None
-    hookable = getattr(optimizer, '_hookable', None)
-    if hookable is None or hookable.has_hooks():
+        return None                       # needs the NaN check + host decision every step
+    if _fusable_hooks(optimizer) is None:
         return None
     if getattr(optimizer, 'target', None) is not model:
         return None
@@ -698,8 +781,6 @@ def _fusion_plan(model, optimizer, zero_fill):
         if rule is None or getattr(rule, 'fused_kind', None) is None:
             return None
         if not rule.enabled or rule._use_fp32_update or rule._hookable.has_hooks():
-            return None
-        if getattr(p, '_loss_scale', None) is not None:
             return None
         ddt = _dev.array_dtype(p.data)
         if isinstance(ddt, str) or ddt not in (np.float16, np.float32, np.float64):

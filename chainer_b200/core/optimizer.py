@@ -192,8 +192,8 @@ class UpdateRule(object):
             if loss_scale is not None and param.grad is not None:
                 from chainer_b200 import _lib
                 g = param.grad
-                _lib.get().gp_scale(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
-                                    _dev.array_size(g), 1.0 / loss_scale, 0)
+                _lib.get().gp_divide(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
+                                     _dev.array_size(g), float(loss_scale), 0)
         self._hookable.call_hooks('pre', (self, param))
         self.update_core(param)
         self._hookable.call_hooks('post', (self, param))
@@ -269,7 +269,12 @@ class Optimizer(object):
             self.call_hook(hook)
 
     def call_hook(self, hook):
-        hook(self)
+        # ``optimizer.py:706-711``
+        if getattr(hook, 'call_for_each_param', False):
+            for param in self.target.params():
+                hook(param.update_rule, param)
+        else:
+            hook(self)
 
     def loss_scaling(self, interval=1000, scale=None):
         """``optimizer.py:736-761``."""

@@ -267,6 +267,7 @@ template <> struct Arith<float> {
   static __device__ __forceinline__ C mul(C a, C b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ C add(C a, C b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ C sub(C a, C b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ C div(C a, C b) { return __fdiv_rn(a, b); }
 };
 template <> struct Arith<__half> {
   using C = float;
@@ -275,6 +276,9 @@ template <> struct Arith<__half> {
   static __device__ __forceinline__ C mul(C a, C b) { return r(__fmul_rn(a, b)); }
   static __device__ __forceinline__ C add(C a, C b) { return r(__fadd_rn(a, b)); }
   static __device__ __forceinline__ C sub(C a, C b) { return r(__fsub_rn(a, b)); }
+  // float has 24 >= 2*11+2 bits: rounding the float quotient to half is the
+  // correctly rounded half quotient
+  static __device__ __forceinline__ C div(C a, C b) { return r(__fdiv_rn(a, b)); }
 };
 template <> struct Arith<double> {
   using C = double;
@@ -282,6 +286,47 @@ template <> struct Arith<double> {
   static __device__ __forceinline__ C mul(C a, C b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ C add(C a, C b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ C sub(C a, C b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ C div(C a, C b) { return __ddiv_rn(a, b); }
+};
+
+// ------------------------------------------- fused pre-update gradient hooks --
+// What GradientMethod.update (chainer/optimizer.py:857-894) and UpdateRule.update
+// (:286-291) do to a gradient between the mean and update_core when the optimizer
+// carries the hooks [GradientClipping][, WeightDecay] and static loss scaling:
+//   g *= rate            optimizer_hooks/gradient_clipping.py:84-106 (rate <= 1, device scalar)
+//   g += decay * p       optimizer_hooks/weight_decay.py:44-57 (decay = rate * loss_scale)
+//   g /= loss_scale      optimizer.py:289-291
+// every operation rounded to the parameter's type, as the array expressions are.
+struct HookArgs {
+  const float* clip_rate;  // device pointer (gp_sqnorm output) or nullptr
+  double decay;            // 0: off
+  double loss_scale;       // 0: off
+};
+template <class P, bool H> struct HookRegs;
+template <class P> struct HookRegs<P, false> {
+  using C = typename Carrier<P>::type;
+  __device__ __forceinline__ explicit HookRegs(const HookArgs&) {}
+  __device__ __forceinline__ C apply(C g, C) const { return g; }
+};
+template <class P> struct HookRegs<P, true> {
+  using C = typename Carrier<P>::type;
+  C rate, decay, ls;
+  bool use_rate, use_decay, use_ls;
+  __device__ __forceinline__ explicit HookRegs(const HookArgs& h) {
+    use_rate = h.clip_rate != nullptr;
+    rate = use_rate ? Arith<P>::cst((double)__ldg(h.clip_rate)) : (C)1;
+    use_decay = h.decay != 0.0;
+    decay = Arith<P>::cst(h.decay);
+    use_ls = h.loss_scale != 0.0;
+    ls = Arith<P>::cst(h.loss_scale);
+  }
+  __device__ __forceinline__ C apply(C g, C p) const {
+    using A = Arith<P>;
+    if (use_rate) g = A::mul(g, rate);
+    if (use_decay) g = A::add(g, A::mul(decay, p));
+    if (use_ls) g = A::div(g, ls);
+    return g;
+  }
 };
 
 // intermediate type T of the Adam kernels (adam.py:57-63): float for

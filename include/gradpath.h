@@ -306,6 +306,58 @@ int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elem
 
 /* ---------------------------------------------------------------- tuning -- */
 /* ---------------------------------------------------------------------------
+ * Optimizer hooks and loss scaling fused into the update.
+ *
+ * GradientMethod.update (chainer/optimizer.py:857-894) runs the optimizer-level
+ * hooks over every parameter before the per-parameter updates, and UpdateRule.update
+ * (:286-291) divides by the loss scale.  For the hook lists [GradientClipping],
+ * [WeightDecay] and [GradientClipping, WeightDecay] (registration order) the
+ * `_hooked` update kernels apply, per element, between the mean and update_core:
+ *     g *= *clip_rate          optimizer_hooks/gradient_clipping.py:84-106
+ *     g += weight_decay * p    optimizer_hooks/weight_decay.py:44-57 (pass rate * loss_scale)
+ *     g /= loss_scale          optimizer.py:289-291
+ * each operation rounded to the parameter's dtype; with write_grad, param.grad
+ * receives the transformed gradient, as the in-place hooks leave it.
+ */
+typedef struct gp_hooks_t {
+  const float* clip_rate;   /* DEVICE pointer: &((float*)out)[2] of gp_sqnorm; NULL: no clipping */
+  double weight_decay;      /* 0: off */
+  double loss_scale;        /* 0: off */
+} gp_hooks_t;
+
+int gp_unpack_momentum_sgd_hooked(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                                  const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                                  int64_t elem_end, double scale, double lr, double momentum,
+                                  int write_grad, int layout_hint, const gp_hooks_t* hooks,
+                                  void* stream);
+int gp_unpack_adam_hooked(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                          const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                          int64_t elem_end, double scale, double alpha_t, double one_minus_beta1,
+                          double one_minus_beta2, double eps, double eta,
+                          double weight_decay_rate, double lower, double upper, int adam_flags,
+                          int write_grad, int layout_hint, const gp_hooks_t* hooks, void* stream);
+
+/* Squared L2 norm of `scale * x[0..n)` (x: the allreduced packed buffer, or one
+ * gradient array) -- _sum_sqnorm_grads, gradient_clipping.py:9-52 -- and the
+ * clipping rate min(threshold / sqrt(sum), 1) (:91-101), formed on the device.
+ * out: 16 bytes of device memory {double sqsum; float rate; float norm}.
+ * accumulate != 0 adds to out->sqsum (per-parameter use); rate and norm always
+ * describe the running total.  Deterministic for a given n (fixed grid and order);
+ * double accumulation.  workspace: gp_sqnorm_workspace_bytes() of ZEROED device
+ * memory, reusable across calls on one stream. */
+size_t gp_sqnorm_workspace_bytes(void);
+int gp_sqnorm(const void* x, int dtype, int64_t n_elems, double scale, int accumulate,
+              double threshold, void* workspace, void* out, void* stream);
+/* x *= *d_factor (float on the device), in x's dtype: the unfused `grad *= rate`
+ * of gradient_clipping.py:103-106 */
+int gp_scale_by_device(void* x, int dtype, int64_t n_elems, const void* d_factor, void* stream);
+/* grad += decay * param, in the arrays' dtype: weight_decay.py:55-57, unfused */
+int gp_weight_decay(void* grad, const void* param, int dtype, int64_t n_elems, double decay,
+                    void* stream);
+/* x /= divisor, in x's dtype: `grad /= loss_scale` of chainer/optimizer.py:289-291, unfused */
+int gp_divide(void* x, int dtype, int64_t n_elems, double divisor, void* stream);
+
+/* ---------------------------------------------------------------------------
  * NVSwitch-multicast (NVLS) allreduce of the packed buffer, 4 / 8 ranks on one box
  * (csrc/gp_mc.cu).  Replaces nccl_comm.allReduce of
  * chainermn/communicators/pure_nccl_communicator.py:180-182: rank r reduces its

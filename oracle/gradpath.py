@@ -179,6 +179,40 @@ def momentum_sgd_update(param, grad, v, lr=0.01, momentum=0.9):
     param += v
 
 
+# ------------------------------------------------- optimizer hooks, loss scale --
+def weight_decay_hook(param, grad, rate, loss_scale=None):
+    """WeightDecay.__call__, CPU branch (chainer/optimizer_hooks/weight_decay.py:44-57),
+    in place: ``rate *= param._loss_scale`` (when set); ``g += rate * p``."""
+    if loss_scale is not None:
+        rate = rate * loss_scale
+    grad += rate * param
+
+
+def gradient_clipping_hook(grads, threshold):
+    """GradientClipping.__call__, CPU branch (chainer/optimizer_hooks/
+    gradient_clipping.py:9-52, 84-106), in place on the list of gradient arrays:
+    sqnorm = sum_i g_i.ravel().dot(g_i.ravel()); rate = threshold / sqrt(sqnorm);
+    if rate < 1: g_i *= rate.  Returns the rate (>= 1: nothing was scaled)."""
+    dots = []
+    for g in grads:
+        r = g.ravel()
+        dots.append(r.dot(r))
+    sqnorm = sum(dots)
+    norm = np.sqrt(sqnorm)
+    with np.errstate(divide='ignore'):
+        rate = threshold / norm
+    if rate >= 1:
+        return rate
+    for g in grads:
+        g *= rate
+    return rate
+
+
+def loss_scale_divide(grad, loss_scale):
+    """UpdateRule.update (chainer/optimizer.py:286-291), in place: ``grad /= loss_scale``."""
+    grad /= loss_scale
+
+
 # ---------------------------------------------------------------------- Adam --
 def adam_alpha_t(alpha, beta1, beta2, t):
     """_learning_rate (adam.py:47-54)."""

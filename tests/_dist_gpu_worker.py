@@ -183,6 +183,9 @@ def main():
                                ('momentum_sgd', np.float16, 2e-3)):
         comm.set_config('allreduce_grad_dtype', adt)
         comm.bucket_bytes = 256 << 10                 # several buckets
+        # Adam runs: several pipelined chunks on the peer-memory / multicast paths too
+        comm.p2p_chunk_bytes = (256 << 10) if opt_name == 'adam' else 0
+        comm.mc_chunk_bytes = (256 << 10) if opt_name == 'adam' else None
         rng = np.random.default_rng(7)
         host_p = [(rng.standard_normal(s) * 0.05).astype(np.float32) for _, s in wl]
         m = link_from_named_arrays([(n, t(a + rank)) for (n, _), a in zip(wl, host_p)])

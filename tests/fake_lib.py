@@ -253,6 +253,93 @@ class FakeLib(object):
                 _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
         return 0
 
+    # -- hooks (csrc/gp_hooks.cu, gp_sgd_hooks.cu, gp_adam_hooks.cu) --------------
+    @staticmethod
+    def _apply_hooks(g, p, hooks_addr, pdt):
+        """g (a fresh array in the parameter dtype) after clip-rate, decay and
+        loss-scale division, each rounded to the parameter dtype."""
+        h = _lib.GpHooks.from_address(int(hooks_addr))
+        if h.clip_rate:
+            rate = _view(h.clip_rate, 1, np.float32)[0]
+            g *= pdt.type(rate)
+        if h.weight_decay != 0.0:
+            og.weight_decay_hook(p, g, h.weight_decay)
+        if h.loss_scale != 0.0:
+            og.loss_scale_divide(g, h.loss_scale)
+        return g
+
+    def gp_unpack_momentum_sgd_hooked(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end,
+                                      scale, lr, momentum, write_grad, layout_hint, hooks, stream):
+        self.calls.append(('gp_unpack_momentum_sgd_hooked', (buf_dtype, n, begin, end, scale, lr,
+                                                             momentum, write_grad)))
+        csum, segs = self._tables_of(d_csum, d_segs, n)
+        for j, e0, e1 in self._pieces(csum, n, begin, end):
+            pdt = _ID2DT[int(segs['dtype1'][j])]
+            size = int(csum[j + 1] - csum[j])
+            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt,
+                                segs[j], size)
+            p = _view(int(segs['ptr'][j, 1]), size, pdt)[e0:e1]
+            v = _view(int(segs['ptr'][j, 2]), size, pdt)[e0:e1]
+            g = self._apply_hooks(np.array(g), p, hooks, pdt)
+            og.momentum_sgd_update(p, g, v, lr, momentum)
+            if write_grad:
+                _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
+        return 0
+
+    def gp_unpack_adam_hooked(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale,
+                              alpha_t, omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad,
+                              layout_hint, hooks, stream):
+        self.calls.append(('gp_unpack_adam_hooked', (buf_dtype, n, begin, end, scale, alpha_t, flags,
+                                                     write_grad)))
+        csum, segs = self._tables_of(d_csum, d_segs, n)
+        for j, e0, e1 in self._pieces(csum, n, begin, end):
+            pdt = _ID2DT[int(segs['dtype1'][j])]
+            size = int(csum[j + 1] - csum[j])
+            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt,
+                                segs[j], size)
+            p = _view(int(segs['ptr'][j, 1]), size, pdt)[e0:e1]
+            m = _view(int(segs['ptr'][j, 2]), size, pdt)[e0:e1]
+            v = _view(int(segs['ptr'][j, 3]), size, pdt)[e0:e1]
+            vh = _view(int(segs['ptr'][j, 4]), size, pdt)[e0:e1] if flags & 1 else None
+            g = self._apply_hooks(np.array(g), p, hooks, pdt)
+            _adam_kernel(p, g, m, v, vh, alpha_t, omb1, omb2, eps, eta, wd, lower, upper, flags)
+            if write_grad:
+                _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
+        return 0
+
+    def gp_sqnorm_workspace_bytes(self):
+        return 64
+
+    def gp_sqnorm(self, x, dtype, n, scale, accumulate, threshold, ws, out, stream):
+        self.calls.append(('gp_sqnorm', (dtype, n, scale, accumulate, threshold)))
+        vals = og.scale_buffer(np.array(_buf_read(x, n, dtype)), _ID2DT[dtype], scale)
+        sq = float(np.sum(np.asarray(vals, dtype=np.float64) ** 2))
+        o_d = _view(out, 1, np.float64)
+        o_f = _view(int(out) + 8, 2, np.float32)
+        total = (float(o_d[0]) if accumulate else 0.0) + sq
+        o_d[0] = total
+        norm = np.float32(np.sqrt(total))
+        with np.errstate(divide='ignore'):
+            o_f[0] = min(np.float32(threshold) / norm, np.float32(1)) if threshold > 0 else 1.0
+        o_f[1] = norm
+        return 0
+
+    def gp_scale_by_device(self, x, dtype, n, d_factor, stream):
+        self.calls.append(('gp_scale_by_device', (dtype, n)))
+        v = _view(x, n, _ID2DT[dtype])
+        v *= _ID2DT[dtype].type(_view(d_factor, 1, np.float32)[0])
+        return 0
+
+    def gp_weight_decay(self, grad, param, dtype, n, decay, stream):
+        self.calls.append(('gp_weight_decay', (dtype, n, decay)))
+        og.weight_decay_hook(_view(param, n, _ID2DT[dtype]), _view(grad, n, _ID2DT[dtype]), decay)
+        return 0
+
+    def gp_divide(self, x, dtype, n, divisor, stream):
+        self.calls.append(('gp_divide', (dtype, n, divisor)))
+        og.loss_scale_divide(_view(x, n, _ID2DT[dtype]), divisor)
+        return 0
+
     def gp_scale(self, buffer, dtype, n, scale, stream):
         self.calls.append(('gp_scale', (dtype, n, scale)))
         vals = og.scale_buffer(np.array(_buf_read(buffer, n, dtype)), _ID2DT[dtype], scale)

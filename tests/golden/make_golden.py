@@ -10,6 +10,8 @@ Outputs (committed):
   adam.npz              chainer.optimizers.Adam (+AdamW, AMSGrad, AdaBound, AMSBound)
   naive_mean_grad.npz   chainermn NaiveCommunicator.multi_node_mean_grad, 2 and 3 ranks
   mnbn.npz              MultiNodeBatchNormalization (_MpiImpl) forward/backward, 2 ranks
+  hooks.npz             MomentumSGD / Adam with WeightDecay, GradientClipping hooks and static
+                        loss scaling, f16/f32
 The reference tree is not available on the GPU box, hence fixtures.
 """
 import importlib.util
@@ -85,11 +87,13 @@ class _Net(chainer.Chain):
 SHAPES = [(2, 3), (), (1, 0, 2), (257,), (130,), (8, 3, 3, 3)]
 
 
-def _run_optimizer(make_opt, dtype, n_steps, seed, grad_scale=1e-2):
+def _run_optimizer(make_opt, dtype, n_steps, seed, grad_scale=1e-2, hooks=(), loss_scale=None):
     rng = np.random.default_rng(seed)
     net = _Net(SHAPES, dtype, rng)
     opt = make_opt()
     opt.setup(net)
+    for h in hooks:
+        opt.add_hook(h)
     rec = {}
     names = [n for n, _ in sorted(net.namedparams())]
     for n, p in sorted(net.namedparams()):
@@ -97,11 +101,17 @@ def _run_optimizer(make_opt, dtype, n_steps, seed, grad_scale=1e-2):
     for step in range(n_steps):
         for n, p in sorted(net.namedparams()):
             g = np.asarray(rng.standard_normal(p.shape) * grad_scale).astype(dtype).reshape(p.shape)
+            if loss_scale is not None:
+                # what backward(loss_scale=...) leaves behind (variable.py: _loss_scale)
+                g = np.asarray(g * dtype.type(loss_scale)).astype(dtype).reshape(p.shape)
+                p._loss_scale = loss_scale
             p.grad = g
             rec['grad%d%s' % (step, n)] = g.copy()
         opt.update()
         for n, p in sorted(net.namedparams()):
             rec['param%d%s' % (step, n)] = p.data.copy()
+            if hooks or loss_scale is not None:
+                rec['gradafter%d%s' % (step, n)] = p.grad.copy()
             for k, s in p.update_rule.state.items():
                 rec['state_%s%d%s' % (k, step, n)] = np.array(s, copy=True)
     return names, rec
@@ -116,6 +126,46 @@ def make_momentum_sgd():
             out['%s|%s' % (dtype, k)] = v
     np.savez_compressed(os.path.join(HERE, 'momentum_sgd.npz'), **out)
     print('momentum_sgd', len(out))
+
+
+HOOK_VARIANTS = {
+    # name: (optimizer, hook list factory, loss_scale)
+    'wd': ('sgd', lambda H: [H.WeightDecay(0.05)], None),
+    'clip': ('sgd', lambda H: [H.GradientClipping(0.05)], None),
+    'clip_noop': ('sgd', lambda H: [H.GradientClipping(1e3)], None),
+    'clip_wd': ('sgd', lambda H: [H.GradientClipping(0.05), H.WeightDecay(0.05)], None),
+    'wd_clip': ('sgd', lambda H: [H.WeightDecay(0.05), H.GradientClipping(0.05)], None),
+    'ls128': ('sgd', lambda H: [], 128.0),
+    'ls100_wd': ('sgd', lambda H: [H.WeightDecay(0.05)], 100.0),
+    'ls128_clip_wd': ('sgd', lambda H: [H.GradientClipping(5.0), H.WeightDecay(0.05)], 128.0),
+    'adam_clip_wd': ('adam', lambda H: [H.GradientClipping(0.05), H.WeightDecay(0.05)], None),
+    'adam_ls128_wd': ('adam', lambda H: [H.WeightDecay(0.05)], 128.0),
+}
+
+
+def make_hooks():
+    """MomentumSGD / Adam with optimizer hooks (chainer/optimizer_hooks/weight_decay.py,
+    gradient_clipping.py) and static loss scaling (chainer/optimizer.py:286-291), CPU path."""
+    from chainer import optimizer_hooks as H
+    out = {}
+    for variant, (opt_name, mk, ls) in HOOK_VARIANTS.items():
+        for dtype in ('float32', 'float16'):
+            if opt_name == 'adam' and dtype == 'float16':
+                # the reference's float16 CPU Adam underflows v for clipped gradients and
+                # diverges from its own GPU formula (see make_adam): not a usable vector
+                continue
+            if opt_name == 'sgd':
+                make_opt = lambda: optimizers.MomentumSGD(lr=0.01, momentum=0.9)   # noqa: E731
+                gs = 1e-2
+            else:
+                make_opt = lambda: optimizers.Adam()                               # noqa: E731
+                gs = 0.5 if dtype == 'float16' else 1e-2
+            names, rec = _run_optimizer(make_opt, np.dtype(dtype), 3, 17, grad_scale=gs,
+                                        hooks=mk(H), loss_scale=ls)
+            for k, v in rec.items():
+                out['%s|%s|%s' % (variant, dtype, k)] = v
+    np.savez_compressed(os.path.join(HERE, 'hooks.npz'), **out)
+    print('hooks', len(out))
 
 
 ADAM_VARIANTS = {
@@ -251,3 +301,4 @@ if __name__ == '__main__':
     make_adam()
     make_naive_mean_grad()
     make_mnbn()
+    make_hooks()

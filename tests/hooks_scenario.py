@@ -1,0 +1,65 @@
+"""The hooks.npz scenarios (WeightDecay / GradientClipping / static loss scaling of
+the unmodified reference) replayed through ``create_multi_node_optimizer``; shared
+by the CPU host-logic test (oracle-backed library double) and the GPU API test."""
+import numpy as np
+
+import chainer_b200
+from chainer_b200.core import link as L
+from tests.helpers import assert_bits_equal
+from tests.test_oracle_golden import HOOK_CASES, hooks_golden  # noqa: F401
+
+
+def hook_objects(spec):
+    from chainer_b200 import optimizer_hooks as H
+    return [H.WeightDecay(arg) if kind == 'wd' else H.GradientClipping(arg) for kind, arg in spec]
+
+
+def run_hooks_scenario(variant, dtype, to_arr, to_np, before_step=None, after_step=None):
+    z = hooks_golden()
+    opt_name, spec, ls = HOOK_CASES[variant]
+    pre = '%s|%s|' % (variant, dtype)
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, to_arr(z[pre + 'init' + n])) for n in names])
+    comm = chainer_b200.create_communicator('pure_nccl')
+    actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9) if opt_name == 'sgd' \
+        else chainer_b200.Adam()
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    for h in hook_objects(spec):
+        opt.add_hook(h)
+    if ls is not None:
+        actual.loss_scaling(scale=ls)
+    opt.update()                                       # first call: broadcast only
+    params = dict(sorted(model.namedparams()))
+    clip = any(k == 'clip' for k, _ in spec)
+    # exact: the arithmetic is the oracle's (pinned bit-for-bit to the reference by
+    # test_oracle_golden).  The norm of the clipping hook is accumulated in double
+    # here and in float32 dot products there; Adam runs the GPU formula where the
+    # vectors come from the reference's CPU formula.
+    exact = opt_name == 'sgd' and not clip
+    for step in range(3):
+        for n in names:
+            params[n].grad = to_arr(z[pre + 'grad%d%s' % (step, n)])
+            params[n]._loss_scale = ls
+        if before_step is not None:
+            before_step()
+        opt.update()
+        if after_step is not None:
+            after_step(comm)
+        for n in names:
+            want_p, want_g = z[pre + 'param%d%s' % (step, n)], z[pre + 'gradafter%d%s' % (step, n)]
+            got_p, got_g = to_np(params[n].data), to_np(params[n].grad)
+            if exact:
+                assert_bits_equal(got_p.reshape(want_p.shape), want_p, (variant, step, n))
+                assert_bits_equal(got_g.reshape(want_g.shape), want_g, (variant, step, n, 'grad'))
+            else:
+                tol = 2e-3 if dtype == 'float16' else 2e-6
+                np.testing.assert_allclose(np.asarray(got_g, dtype=np.float64).reshape(want_g.shape),
+                                           np.asarray(want_g, dtype=np.float64), rtol=tol,
+                                           atol=tol * 1e-2, err_msg=str((variant, step, n, 'grad')))
+                ptol = tol if opt_name == 'sgd' else max(tol, 2e-5)
+                np.testing.assert_allclose(np.asarray(got_p, dtype=np.float64).reshape(want_p.shape),
+                                           np.asarray(want_p, dtype=np.float64), rtol=ptol,
+                                           atol=ptol * 1e-2, err_msg=str((variant, step, n)))
+    assert actual.t == 3
+    comm.finalize()

@@ -516,3 +516,83 @@ def test_standalone_update_is_one_launch_per_group(fake):
             og.momentum_sgd_update(q.data, q.grad, v, 0.01 if name == '/d/b' else 0.1, 0.9)
             assert_bits_equal(p.data, q.data, name)
             assert_bits_equal(p.update_rule.state['v'], v, name)
+
+
+def test_pipeline_chunk_bounds():
+    from chainer_b200.communicators.pure_nccl_communicator import PureNcclCommunicator as C
+    assert C._chunk_bounds(1000, 4, 0) == [0, 1000]
+    # ResNet-50 fp32: the automatic multicast chunking is two 4096-aligned halves
+    n = 25557096
+    cb = C._chunk_bounds(n, 4, C._auto_mc_chunk_bytes(n, 4))
+    assert len(cb) == 3 and cb[0] == 0 and cb[-1] == n and cb[1] % 4096 == 0
+    assert abs(cb[1] - n / 2) < 4096
+    # small buffers: one kernel
+    assert C._auto_mc_chunk_bytes(600000, 4) == 0
+    # explicit chunk size: aligned interior bounds, short tail folded into the last chunk
+    cb = C._chunk_bounds(600000, 4, 256 << 10)
+    assert all(b % 4096 == 0 for b in cb[1:-1]) and cb[-1] == 600000
+    sizes = np.diff(cb)
+    assert sizes.min() >= (65536 // 2) and sizes[:-1].max() == 65536
+    for isz in (2, 4, 8):
+        for n in (1, 4095, 4096, 4097, 100003, 25557096):
+            for chunk in (0, 1, 4096, 1 << 20):
+                cb = C._chunk_bounds(n, isz, chunk)
+                assert cb[0] == 0 and cb[-1] == n and all(np.diff(cb) > 0)
+                assert all(b % 4096 == 0 for b in cb[1:-1])
+
+
+# ------------------------------------------- optimizer hooks and loss scaling --
+from tests.hooks_scenario import HOOK_CASES, hook_objects, hooks_golden, run_hooks_scenario  # noqa: E402
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'float16'])
+@pytest.mark.parametrize('variant', sorted(HOOK_CASES))
+def test_hooks_and_loss_scale_through_the_multi_node_optimizer(fake, variant, dtype):
+    """WeightDecay / GradientClipping hooks and static loss scaling behind
+    create_multi_node_optimizer reproduce the unmodified reference (hooks.npz):
+    fused into the update kernel for [clip], [wd], [clip, wd]; the reference
+    sequence of hook kernels for [wd, clip]."""
+    opt_name, spec, ls = HOOK_CASES[variant]
+    if opt_name == 'adam' and dtype == 'float16':
+        pytest.skip('no reference vector: float16 CPU Adam underflows (make_golden.py)')
+    fusable = [k for k, _ in spec] != ['wd', 'clip']
+    clip = any(k == 'clip' for k, _ in spec)
+    kernel = 'gp_unpack_momentum_sgd' if opt_name == 'sgd' else 'gp_unpack_adam'
+
+    def before_step():
+        fake.calls[:] = []
+
+    def after_step(comm):
+        called = [c[0] for c in fake.calls]
+        if fusable:
+            assert (kernel + '_hooked') in called and kernel not in called
+            assert ('gp_sqnorm' in called) == clip
+            assert 'gp_weight_decay' not in called and 'gp_scale_by_device' not in called
+            assert 'gp_divide' not in called
+        else:
+            assert 'gp_weight_decay' in called and 'gp_scale_by_device' in called
+
+    run_hooks_scenario(variant, dtype, lambda a: a.copy(), np.asarray, before_step, after_step)
+
+
+def test_standalone_optimizer_hooks(fake):
+    """optimizer.update() without a communicator: call_for_each_param hooks and
+    optimizer-level hooks run as in chainer/optimizer.py:706-711 (unfused kernels)."""
+    z = hooks_golden()
+    pre = 'clip_wd|float32|'
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, z[pre + 'init' + n].copy()) for n in names])
+    opt = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9)
+    opt.setup(model)
+    for h in hook_objects(HOOK_CASES['clip_wd'][1]):
+        opt.add_hook(h)
+    params = dict(sorted(model.namedparams()))
+    for step in range(3):
+        for n in names:
+            params[n].grad = z[pre + 'grad%d%s' % (step, n)].copy()
+        opt.update()
+        for n in names:
+            np.testing.assert_allclose(params[n].data, z[pre + 'param%d%s' % (step, n)],
+                                       rtol=2e-6, atol=2e-8)
+            np.testing.assert_allclose(params[n].grad, z[pre + 'gradafter%d%s' % (step, n)],
+                                       rtol=2e-6, atol=2e-8)
