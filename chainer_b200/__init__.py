@@ -16,4 +16,5 @@ from chainer_b200.communicators import create_communicator  # NOQA
 from chainer_b200.optimizers import create_multi_node_optimizer  # NOQA
 from chainer_b200.core import Chain, ChainList, Link, Parameter  # NOQA
 from chainer_b200.core.optimizers import Adam, MomentumSGD  # NOQA
+from chainer_b200.core.optimizers import SGD, CorrectedMomentumSGD, NesterovAG  # NOQA
 from chainer_b200.config import get_dtype, is_debug, set_debug  # NOQA

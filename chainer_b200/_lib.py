@@ -43,6 +43,9 @@ assert SEG_DTYPE.itemsize == 64
 
 
 
+RULE_SGD, RULE_CORRECTED_MOMENTUM, RULE_NESTEROV_AG = 0, 1, 2
+
+
 class GpHooks(ctypes.Structure):
     """ctypes mirror of ``gp_hooks_t`` (include/gradpath.h)."""
     _fields_ = [('clip_rate', ctypes.c_void_p), ('weight_decay', ctypes.c_double),
@@ -119,6 +122,9 @@ PROTOTYPES = {
                                       c_double, c_double, c_double, c_double, c_double, c_double,
                                       c_double, c_double, c_double, c_int, c_int, c_int,
                                       c_void_p, c_void_p]),
+    'gp_unpack_sgd_family': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                     c_double, c_int, c_double, c_double, c_int, c_int, c_void_p,
+                                     c_void_p]),
     'gp_sqnorm_workspace_bytes': (c_size_t, []),
     'gp_sqnorm': (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_double, c_void_p, c_void_p,
                           c_void_p]),
@@ -160,7 +166,7 @@ KERNEL_FUNCS = frozenset([
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
     'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce',
     'gp_unpack_momentum_sgd_hooked', 'gp_unpack_adam_hooked', 'gp_sqnorm', 'gp_scale_by_device',
-    'gp_weight_decay', 'gp_divide'])
+    'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family'])
 
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',

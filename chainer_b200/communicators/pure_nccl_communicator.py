@@ -680,6 +680,9 @@ class _FusedPlan(object):
                 else:
                     lib.gp_unpack_momentum_sgd(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
                                                begin, end, scale, key[1], key[2], wg, hint, sp)
+            elif key[0] == 'sgd_family':
+                lib.gp_unpack_sgd_family(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin,
+                                         end, scale, key[1], key[2], key[3], wg, hint, hk_addr, sp)
             elif hooked:
                 lib.gp_unpack_adam_hooked(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params, begin,
                                           end, scale, key[1], key[2], key[3], key[4], key[5],

@@ -63,6 +63,10 @@ def update(opt):
             lib.gp_unpack_momentum_sgd(None, dt_id, pd.d_csum, pd.d_segs, pd.n_params, 0,
                                        pd.n_elems, 1.0, k[1], k[2], 0,
                                        pd.layout_hint(np.dtype(key[0])), 0)
+        elif k[0] == 'sgd_family':
+            lib.gp_unpack_sgd_family(None, dt_id, pd.d_csum, pd.d_segs, pd.n_params, 0, pd.n_elems,
+                                     1.0, k[1], k[2], k[3], 0, pd.layout_hint(np.dtype(key[0])),
+                                     None, 0)
         else:
             lib.gp_unpack_adam(None, dt_id, pd.d_csum, pd.d_segs, pd.n_params, 0, pd.n_elems, 1.0,
                                k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], k[9], 0,

@@ -337,6 +337,22 @@ int gp_unpack_adam_hooked(const void* buffer, int buf_dtype, const int64_t* d_cs
                           double weight_decay_rate, double lower, double upper, int adam_flags,
                           int write_grad, int layout_hint, const gp_hooks_t* hooks, void* stream);
 
+/* The other first-order rules with MomentumSGD's shape (csrc/gp_sgd_family.cu), same
+ * tables (ptr[0] grad, ptr[1] param, ptr[2] v), hooks optional (NULL: none):
+ *   GP_RULE_SGD                 param -= lr * grad                  chainer/optimizers/sgd.py:45-63
+ *   GP_RULE_CORRECTED_MOMENTUM  v = momentum*v - grad; param += lr*v
+ *                                                     chainer/optimizers/corrected_momentum_sgd.py:61-89
+ *   GP_RULE_NESTEROV_AG         v = momentum*v - lr*grad; param += momentum^2 * v;
+ *                               param -= (1+momentum)*lr * grad     chainer/optimizers/nesterov_ag.py:60-71
+ * arithmetic in the parameter dtype in the order of update_core_cpu. */
+#define GP_RULE_SGD 0
+#define GP_RULE_CORRECTED_MOMENTUM 1
+#define GP_RULE_NESTEROV_AG 2
+int gp_unpack_sgd_family(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                         const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                         int64_t elem_end, double scale, int rule, double lr, double momentum,
+                         int write_grad, int layout_hint, const gp_hooks_t* hooks, void* stream);
+
 /* Squared L2 norm of `scale * x[0..n)` (x: the allreduced packed buffer, or one
  * gradient array) -- _sum_sqnorm_grads, gradient_clipping.py:9-52 -- and the
  * clipping rate min(threshold / sqrt(sum), 1) (:91-101), formed on the device.

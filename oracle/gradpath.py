@@ -179,6 +179,30 @@ def momentum_sgd_update(param, grad, v, lr=0.01, momentum=0.9):
     param += v
 
 
+# ------------------------------------------ SGD, CorrectedMomentumSGD, NesterovAG --
+def sgd_update(param, grad, lr=0.01):
+    """SGDRule.update_core_cpu (chainer/optimizers/sgd.py:45-52), in place."""
+    param -= lr * grad
+
+
+def corrected_momentum_sgd_update(param, grad, v, lr=0.01, momentum=0.9):
+    """CorrectedMomentumSGDRule.update_core_cpu
+    (chainer/optimizers/corrected_momentum_sgd.py:61-75), in place."""
+    v *= momentum
+    v -= grad
+    param += lr * v
+
+
+def nesterov_ag_update(param, grad, v, lr=0.01, momentum=0.9):
+    """NesterovAGRule.update_core_cpu (chainer/optimizers/nesterov_ag.py:60-71), in
+    place.  (The reference's GPU kernel, :73-84, adds `m*m*v - (1+m)*lr*grad` to the
+    parameter in one expression: one rounding less, tolerance-level difference.)"""
+    v *= momentum
+    v -= lr * grad
+    param += momentum * momentum * v
+    param -= (1 + momentum) * lr * grad
+
+
 # ------------------------------------------------- optimizer hooks, loss scale --
 def weight_decay_hook(param, grad, rate, loss_scale=None):
     """WeightDecay.__call__, CPU branch (chainer/optimizer_hooks/weight_decay.py:44-57),

@@ -307,6 +307,32 @@ class FakeLib(object):
                 _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
         return 0
 
+    def gp_unpack_sgd_family(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, rule,
+                             lr, momentum, write_grad, layout_hint, hooks, stream):
+        self.calls.append(('gp_unpack_sgd_family', (buf_dtype, n, begin, end, scale, rule, lr,
+                                                    momentum, write_grad)))
+        csum, segs = self._tables_of(d_csum, d_segs, n)
+        for j, e0, e1 in self._pieces(csum, n, begin, end):
+            pdt = _ID2DT[int(segs['dtype1'][j])]
+            size = int(csum[j + 1] - csum[j])
+            g = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, pdt,
+                                segs[j], size)
+            p = _view(int(segs['ptr'][j, 1]), size, pdt)[e0:e1]
+            g = np.array(g)
+            if hooks:
+                g = self._apply_hooks(g, p, hooks, pdt)
+            if rule == 0:
+                og.sgd_update(p, g, lr)
+            else:
+                v = _view(int(segs['ptr'][j, 2]), size, pdt)[e0:e1]
+                if rule == 1:
+                    og.corrected_momentum_sgd_update(p, g, v, lr, momentum)
+                else:
+                    og.nesterov_ag_update(p, g, v, lr, momentum)
+            if write_grad:
+                _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
+        return 0
+
     def gp_sqnorm_workspace_bytes(self):
         return 64
 

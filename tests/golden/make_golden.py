@@ -10,6 +10,7 @@ Outputs (committed):
   adam.npz              chainer.optimizers.Adam (+AdamW, AMSGrad, AdaBound, AMSBound)
   naive_mean_grad.npz   chainermn NaiveCommunicator.multi_node_mean_grad, 2 and 3 ranks
   mnbn.npz              MultiNodeBatchNormalization (_MpiImpl) forward/backward, 2 ranks
+  sgd_family.npz        SGD, CorrectedMomentumSGD, NesterovAG (+ hooks), f16/f32/f64
   hooks.npz             MomentumSGD / Adam with WeightDecay, GradientClipping hooks and static
                         loss scaling, f16/f32
 The reference tree is not available on the GPU box, hence fixtures.
@@ -168,6 +169,29 @@ def make_hooks():
     print('hooks', len(out))
 
 
+def make_sgd_family():
+    """chainer.optimizers.SGD / CorrectedMomentumSGD / NesterovAG, 3 steps, f16/f32/f64, and
+    each once more with [GradientClipping, WeightDecay] hooks (float32)."""
+    from chainer import optimizer_hooks as H
+    out = {}
+    makers = {
+        'sgd': lambda: optimizers.SGD(lr=0.05),
+        'corrected': lambda: optimizers.CorrectedMomentumSGD(lr=0.05, momentum=0.8),
+        'nesterov': lambda: optimizers.NesterovAG(lr=0.05, momentum=0.8),
+    }
+    for rule, mk in makers.items():
+        for dtype in ('float32', 'float16', 'float64'):
+            names, rec = _run_optimizer(mk, np.dtype(dtype), 3, 19)
+            for k, v in rec.items():
+                out['%s|%s|%s' % (rule, dtype, k)] = v
+        names, rec = _run_optimizer(mk, np.dtype('float32'), 3, 23,
+                                    hooks=[H.GradientClipping(0.05), H.WeightDecay(0.05)])
+        for k, v in rec.items():
+            out['%s_clip_wd|float32|%s' % (rule, k)] = v
+    np.savez_compressed(os.path.join(HERE, 'sgd_family.npz'), **out)
+    print('sgd_family', len(out))
+
+
 ADAM_VARIANTS = {
     'adam': dict(),
     'adamw': dict(eta=0.5, weight_decay_rate=0.1),
@@ -302,3 +326,4 @@ if __name__ == '__main__':
     make_naive_mean_grad()
     make_mnbn()
     make_hooks()
+    make_sgd_family()

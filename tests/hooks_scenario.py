@@ -6,7 +6,7 @@ import numpy as np
 import chainer_b200
 from chainer_b200.core import link as L
 from tests.helpers import assert_bits_equal
-from tests.test_oracle_golden import HOOK_CASES, hooks_golden  # noqa: F401
+from tests.test_oracle_golden import HOOK_CASES, _npz, hooks_golden  # noqa: F401
 
 
 def hook_objects(spec):
@@ -63,3 +63,54 @@ def run_hooks_scenario(variant, dtype, to_arr, to_np, before_step=None, after_st
                                            atol=ptol * 1e-2, err_msg=str((variant, step, n)))
     assert actual.t == 3
     comm.finalize()
+
+
+def _family_optimizer(rule):
+    return {'sgd': lambda: chainer_b200.SGD(lr=0.05),
+            'corrected': lambda: chainer_b200.CorrectedMomentumSGD(lr=0.05, momentum=0.8),
+            'nesterov': lambda: chainer_b200.NesterovAG(lr=0.05, momentum=0.8)}[rule]()
+
+
+def run_family_scenario(rule, dtype, hooks, multi_node, to_arr, to_np, after_step=None):
+    """sgd_family.npz (the unmodified reference) replayed through the product."""
+    z = _npz('sgd_family.npz')
+    pre = '%s%s|%s|' % (rule, '_clip_wd' if hooks else '', dtype)
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, to_arr(z[pre + 'init' + n])) for n in names])
+    actual = _family_optimizer(rule)
+    comm = None
+    if multi_node:
+        comm = chainer_b200.create_communicator('pure_nccl')
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    else:
+        opt = actual
+    opt.setup(model)
+    if hooks:
+        for h in hook_objects([('clip', 0.05), ('wd', 0.05)]):
+            opt.add_hook(h)
+    if multi_node:
+        opt.update()                                   # first call: broadcast only
+    params = dict(sorted(model.namedparams()))
+    for step in range(3):
+        for n in names:
+            params[n].grad = to_arr(z[pre + 'grad%d%s' % (step, n)])
+        opt.update()
+        if after_step is not None:
+            after_step(comm)
+        for n in names:
+            want = z[pre + 'param%d%s' % (step, n)]
+            got = to_np(params[n].data).reshape(want.shape)
+            if hooks:       # the norm is accumulated in double here, float32 dots there
+                np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-8)
+            else:
+                assert_bits_equal(got, want, (rule, dtype, step, n))
+            if rule != 'sgd':
+                want_v = z[pre + 'state_v%d%s' % (step, n)]
+                got_v = to_np(params[n].update_rule.state['v']).reshape(want_v.shape)
+                if hooks:
+                    np.testing.assert_allclose(got_v, want_v, rtol=2e-6, atol=2e-8)
+                else:
+                    assert_bits_equal(got_v, want_v, (rule, dtype, step, n, 'v'))
+    assert actual.t == 3
+    if comm is not None:
+        comm.finalize()

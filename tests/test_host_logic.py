@@ -596,3 +596,35 @@ def test_standalone_optimizer_hooks(fake):
                                        rtol=2e-6, atol=2e-8)
             np.testing.assert_allclose(params[n].grad, z[pre + 'gradafter%d%s' % (step, n)],
                                        rtol=2e-6, atol=2e-8)
+
+
+# ------------------------------------------ SGD, CorrectedMomentumSGD, NesterovAG --
+from tests.hooks_scenario import run_family_scenario  # noqa: E402
+
+
+@pytest.mark.parametrize('multi_node', [True, False])
+@pytest.mark.parametrize('dtype,hooks', [('float32', False), ('float16', False), ('float64', False),
+                                         ('float32', True)])
+@pytest.mark.parametrize('rule', ['sgd', 'corrected', 'nesterov'])
+def test_sgd_family_rules(fake, rule, dtype, hooks, multi_node):
+    """SGD / CorrectedMomentumSGD / NesterovAG reproduce the reference bit-for-bit,
+    fused behind the multi-node optimizer (one gp_unpack_sgd_family launch) and as a
+    stand-alone multi-tensor optimizer.update()."""
+    if multi_node and dtype == 'float64':
+        pytest.skip('bcast_data and the allreduce buffer are float32 (chainer.get_dtype()): '
+                    'float64 parameters do not stay bit-identical behind the communicator')
+
+    def after_step(comm):
+        called = [c[0] for c in fake.calls]
+        if 'gp_pack' in called:                # drop the initial broadcast's pack / unpack
+            called = called[len(called) - 1 - called[::-1].index('gp_pack'):]
+        assert 'gp_unpack_sgd_family' in called
+        if multi_node:
+            assert 'gp_unpack_scale' not in called           # fused, not the reference sequence
+            assert ('gp_sqnorm' in called) == hooks
+        n_launch = called.count('gp_unpack_sgd_family')
+        assert n_launch == 1, called
+        fake.calls[:] = []
+
+    fake.calls[:] = []
+    run_family_scenario(rule, dtype, hooks, multi_node, lambda a: a.copy(), np.asarray, after_step)

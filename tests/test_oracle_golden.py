@@ -298,3 +298,38 @@ def test_hooks_and_loss_scale_match_reference(variant, dtype):
     def check(step, name, what, got, want):
         assert_bits_equal(got, want, (variant, dtype, step, name, what))
     replay_hooks(hooks_golden(), variant, dtype, check)
+
+
+# ------------------------------------------ SGD, CorrectedMomentumSGD, NesterovAG --
+FAMILY = {
+    'sgd': (lambda p, g, s: og.sgd_update(p, g, 0.05)),
+    'corrected': (lambda p, g, s: og.corrected_momentum_sgd_update(p, g, s['v'], 0.05, 0.8)),
+    'nesterov': (lambda p, g, s: og.nesterov_ag_update(p, g, s['v'], 0.05, 0.8)),
+}
+
+
+def replay_family(z, rule, dtype, hooks, check):
+    pre = '%s%s|%s|' % (rule, '_clip_wd' if hooks else '', dtype)
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    params = [z[pre + 'init' + n].copy() for n in names]
+    st = [dict(v=np.zeros_like(p)) for p in params]
+    for step in range(3):
+        grads = [z[pre + 'grad%d%s' % (step, n)].copy() for n in names]
+        if hooks:
+            og.gradient_clipping_hook(grads, 0.05)
+            for p, g in zip(params, grads):
+                og.weight_decay_hook(p, g, 0.05)
+        for n, p, g, s in zip(names, params, grads, st):
+            FAMILY[rule](p, g, s)
+            check(step, n, 'param', p, z[pre + 'param%d%s' % (step, n)])
+            if rule != 'sgd':
+                check(step, n, 'v', s['v'], z[pre + 'state_v%d%s' % (step, n)])
+
+
+@pytest.mark.parametrize('dtype,hooks', [('float32', False), ('float16', False), ('float64', False),
+                                         ('float32', True)])
+@pytest.mark.parametrize('rule', sorted(FAMILY))
+def test_sgd_family_matches_reference(rule, dtype, hooks):
+    def check(step, name, what, got, want):
+        assert_bits_equal(got, want, (rule, dtype, step, name, what))
+    replay_family(_npz('sgd_family.npz'), rule, dtype, hooks, check)
