@@ -295,6 +295,50 @@ class Optimizer(object):
     def set_loss_scale(self, loss_scale):
         self.loss_scaling(scale=loss_scale)
 
+    def check_nan_in_grads(self):
+        """``optimizer.py:763-776``: with dynamic loss scaling, look for non-finite
+        gradients.  One finiteness kernel per gradient writes its own flag word; ONE
+        small read-back tells which parameters overflowed (the reference
+        synchronises once per parameter)."""
+        self._loss_scaling_isnan = False
+        if not self._loss_scaling_is_dynamic:
+            return
+        from chainer_b200 import _lib
+        lib = _lib.get()
+        named = [(name, p) for name, p in self.target.namedparams() if p.grad is not None]
+        if not named:
+            return
+        flags = _dev.DeviceArray.zeros((len(named),), np.int32)
+        for i, (_, p) in enumerate(named):
+            g = p.grad
+            lib.gp_check_finite(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
+                                _dev.array_size(g), flags.data.ptr + 4 * i, 0)
+        host = flags.get()
+        for (name, _), bad in zip(named, host):
+            if bad:
+                self._loss_scaling_isnan = True
+                self._loss_scaling_isnan_ever = True
+                warnings.warn(
+                    'Non finite number found in param.grad of {}'
+                    ' (iteration: {}, loss_scale: {})'
+                    .format(name, self.t, self._loss_scale))
+
+    def is_safe_to_update(self):
+        return not getattr(self, '_loss_scaling_isnan', False)
+
+    def update_loss_scale(self):
+        """``optimizer.py:781-791``."""
+        if not self._loss_scaling_is_dynamic:
+            return
+        if self._loss_scaling_isnan:
+            multiplier = 0.5
+        elif self._loss_scaling_isnan_ever:
+            multiplier = self._loss_scaling_multiplier
+        else:
+            multiplier = 2.0
+        self._loss_scale = max(1, min(self._loss_scale_max,
+                                      self._loss_scale * multiplier))
+
     def serialize(self, serializer):
         self.t = serializer('t', self.t)
         self.epoch = serializer('epoch', self.epoch)
@@ -343,15 +387,18 @@ class GradientMethod(Optimizer):
             del loss
 
         self.reallocate_cleared_grads()
+        self.check_nan_in_grads()
         self.call_hooks('pre')
 
         self.t += 1
-        if not self._multi_tensor_update():
-            for param in self.target.params():
-                param.update()
+        if self.is_safe_to_update():
+            if not self._multi_tensor_update():
+                for param in self.target.params():
+                    param.update()
 
         self.reallocate_cleared_grads()
         self.call_hooks('post')
+        self.update_loss_scale()
 
     def _multi_tensor_update(self):
         """All parameter updates of this step as ONE launch per (dtype, hyperparameter)

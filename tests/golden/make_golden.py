@@ -11,6 +11,7 @@ Outputs (committed):
   naive_mean_grad.npz   chainermn NaiveCommunicator.multi_node_mean_grad, 2 and 3 ranks
   mnbn.npz              MultiNodeBatchNormalization (_MpiImpl) forward/backward, 2 ranks
   sgd_family.npz        SGD, CorrectedMomentumSGD, NesterovAG (+ hooks), f16/f32/f64
+  dynamic_loss_scale.npz  MomentumSGD with dynamic loss scaling and a non-finite gradient
   hooks.npz             MomentumSGD / Adam with WeightDecay, GradientClipping hooks and static
                         loss scaling, f16/f32
 The reference tree is not available on the GPU box, hence fixtures.
@@ -192,6 +193,41 @@ def make_sgd_family():
     print('sgd_family', len(out))
 
 
+def make_dynamic_loss_scale():
+    """MomentumSGD with dynamic loss scaling (chainer/optimizer.py:736-791, 881-894): 6
+    steps, a non-finite gradient in step 2; records the loss scale and the parameters."""
+    out = {}
+    for dtype in ('float32', 'float16'):
+        dt = np.dtype(dtype)
+        rng = np.random.default_rng(29)
+        net = _Net(SHAPES, dt, rng)
+        opt = optimizers.MomentumSGD(lr=0.01, momentum=0.9)
+        opt.setup(net)
+        opt.loss_scaling(interval=2)
+        for n, p in sorted(net.namedparams()):
+            out['%s|init%s' % (dtype, n)] = p.data.copy()
+        scales = []
+        for step in range(6):
+            ls = opt._loss_scale
+            for n, p in sorted(net.namedparams()):
+                g = np.asarray(rng.standard_normal(p.shape) * 1e-2).astype(dt).reshape(p.shape)
+                if step == 2 and n == '/p03':
+                    g[5] = np.inf
+                out['%s|grad%d%s' % (dtype, step, n)] = g.copy()        # unscaled
+                p.grad = np.asarray(g * dt.type(ls)).astype(dt).reshape(p.shape)
+                p._loss_scale = ls
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                opt.update()
+            scales.append(opt._loss_scale)
+            for n, p in sorted(net.namedparams()):
+                out['%s|param%d%s' % (dtype, step, n)] = p.data.copy()
+        out['%s|scales' % dtype] = np.asarray(scales, dtype=np.float64)
+        out['%s|t' % dtype] = np.asarray([opt.t] + [p.update_rule.t for _, p in sorted(net.namedparams())])
+    np.savez_compressed(os.path.join(HERE, 'dynamic_loss_scale.npz'), **out)
+    print('dynamic_loss_scale', len(out), out['float32|scales'], out['float32|t'])
+
+
 ADAM_VARIANTS = {
     'adam': dict(),
     'adamw': dict(eta=0.5, weight_decay_rate=0.1),
@@ -327,3 +363,4 @@ if __name__ == '__main__':
     make_mnbn()
     make_hooks()
     make_sgd_family()
+    make_dynamic_loss_scale()

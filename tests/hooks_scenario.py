@@ -114,3 +114,47 @@ def run_family_scenario(rule, dtype, hooks, multi_node, to_arr, to_np, after_ste
     assert actual.t == 3
     if comm is not None:
         comm.finalize()
+
+
+def run_dynamic_loss_scale(dtype, multi_node, to_arr, to_np):
+    """dynamic_loss_scale.npz: MomentumSGD with dynamic loss scaling; step 2 carries a
+    non-finite gradient (update skipped, scale halved, then grown by 2**(1/interval))."""
+    import warnings
+    z = _npz('dynamic_loss_scale.npz')
+    pre = dtype + '|'
+    dt = np.dtype(dtype)
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, to_arr(z[pre + 'init' + n])) for n in names])
+    actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9)
+    comm = None
+    if multi_node:
+        comm = chainer_b200.create_communicator('pure_nccl')
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    else:
+        opt = actual
+    opt.setup(model)
+    actual.loss_scaling(interval=2)
+    if multi_node:
+        opt.update()
+    params = dict(sorted(model.namedparams()))
+    scales = []
+    for step in range(6):
+        ls = actual._loss_scale
+        for n in names:
+            g = z[pre + 'grad%d%s' % (step, n)]
+            params[n].grad = to_arr(np.asarray(g * dt.type(ls)).astype(dt).reshape(g.shape))
+            params[n]._loss_scale = ls
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter('always')
+            opt.update()
+        assert any('Non finite number found in param.grad of /p03' in str(x.message)
+                   for x in w) == (step == 2)
+        scales.append(actual._loss_scale)
+        for n in names:
+            want = z[pre + 'param%d%s' % (step, n)]
+            assert_bits_equal(to_np(params[n].data).reshape(want.shape), want, (dtype, step, n))
+    np.testing.assert_array_equal(np.asarray(scales, dtype=np.float64), z[pre + 'scales'])
+    ts = [actual.t] + [p.update_rule.t for _, p in sorted(model.namedparams())]
+    np.testing.assert_array_equal(np.asarray(ts), z[pre + 't'])
+    if comm is not None:
+        comm.finalize()

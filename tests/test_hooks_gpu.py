@@ -303,3 +303,10 @@ def test_clipping_hook_standalone_and_norm_readback():
         og.momentum_sgd_update(q, g, v)
         np.testing.assert_allclose(to_host(p.data), q, rtol=2e-6, atol=1e-9)
         np.testing.assert_allclose(to_host(p.grad), g, rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('multi_node', [True, False])
+@pytest.mark.parametrize('dtype', ['float32', 'float16'])
+def test_dynamic_loss_scaling_gpu(dtype, multi_node):
+    from tests.hooks_scenario import run_dynamic_loss_scale
+    run_dynamic_loss_scale(dtype, multi_node, lambda a: to_dev(np.array(a)), to_host)

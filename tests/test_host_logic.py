@@ -628,3 +628,13 @@ def test_sgd_family_rules(fake, rule, dtype, hooks, multi_node):
 
     fake.calls[:] = []
     run_family_scenario(rule, dtype, hooks, multi_node, lambda a: a.copy(), np.asarray, after_step)
+
+
+@pytest.mark.parametrize('multi_node', [True, False])
+@pytest.mark.parametrize('dtype', ['float32', 'float16'])
+def test_dynamic_loss_scaling(fake, dtype, multi_node):
+    """check_nan_in_grads / is_safe_to_update / update_loss_scale
+    (chainer/optimizer.py:763-791, 881-894) reproduce the reference's loss-scale
+    trajectory, skipped update and parameters bit-for-bit."""
+    from tests.hooks_scenario import run_dynamic_loss_scale
+    run_dynamic_loss_scale(dtype, multi_node, lambda a: a.copy(), np.asarray)
