@@ -11,6 +11,7 @@ __version__ = '0.1.0'
 
 from chainer_b200 import config  # NOQA
 from chainer_b200 import optimizer_hooks  # NOQA
+from chainer_b200 import extensions  # NOQA
 from chainer_b200.communicators import CommunicatorBase  # NOQA
 from chainer_b200.communicators import create_communicator  # NOQA
 from chainer_b200.optimizers import create_multi_node_optimizer  # NOQA

@@ -111,6 +111,7 @@ class Link(object):
 
     def __init__(self, **params):
         self._params = []
+        self._persistent = []
         self._within_init_scope = False
         self.name = None
         for name, value in params.items():
@@ -139,6 +140,24 @@ class Link(object):
             setattr(self, name, p)
         return p
 
+    def add_persistent(self, name, value):
+        """``link.py:463-481``: a value saved with the link that is not a parameter
+        (running statistics of batch normalisation, counters)."""
+        if name in self.__dict__ and name not in self._persistent:
+            raise AttributeError('cannot register a new persistent value %s: attribute exists'
+                                 % name)
+        if name not in self._persistent:
+            self._persistent.append(name)
+        super(Link, self).__setattr__(name, value)
+
+    def register_persistent(self, name):
+        """``link.py:483-497``: mark an existing attribute as persistent."""
+        if not hasattr(self, name):
+            raise AttributeError('cannot register non-existent attribute %s as a persistent '
+                                 'value' % name)
+        if name not in self._persistent:
+            self._persistent.append(name)
+
     def params(self, include_uninit=True):
         for name in sorted(self._params):
             p = self.__dict__[name]
@@ -154,6 +173,11 @@ class Link(object):
     def links(self, skipself=False):
         if not skipself:
             yield self
+
+    def namedlinks(self, skipself=False):
+        """``link.py:704-715``: (path, link) pairs, the link itself at '/'."""
+        if not skipself:
+            yield '/', self
 
     def children(self):
         return iter(())
@@ -209,6 +233,16 @@ class Chain(Link):
             for link in self.__dict__[name].links():
                 yield link
 
+    def namedlinks(self, skipself=False):
+        if not skipself:
+            yield '/', self
+        for name in sorted(self._children):
+            child = self.__dict__[name]
+            prefix = '/' + name
+            yield prefix, child
+            for path, link in child.namedlinks(True):
+                yield prefix + path, link
+
     def children(self):
         for name in sorted(self._children):
             yield self.__dict__[name]
@@ -256,6 +290,15 @@ class ChainList(Link):
         for child in self._children:
             for link in child.links():
                 yield link
+
+    def namedlinks(self, skipself=False):
+        if not skipself:
+            yield '/', self
+        for idx, child in enumerate(self._children):
+            prefix = '/{}'.format(idx)
+            yield prefix, child
+            for path, link in child.namedlinks(True):
+                yield prefix + path, link
 
     def children(self):
         return iter(self._children)

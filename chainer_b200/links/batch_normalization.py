@@ -81,9 +81,10 @@ class MultiNodeBatchNormalization(link.Link):
         tdt = {np.dtype(np.float16): torch.float16, np.dtype(np.float32): torch.float32,
                np.dtype(np.float64): torch.float64}[np.dtype(self._highprec_dtype)]
         self.comm = comm
-        self.avg_mean = torch.zeros(size, dtype=tdt, device=device)
-        self.avg_var = torch.zeros(size, dtype=tdt, device=device)
-        self.N = 0
+        # persistents, as in the reference (links/batch_normalization.py:57-61)
+        self.add_persistent('avg_mean', torch.zeros(size, dtype=tdt, device=device))
+        self.add_persistent('avg_var', torch.zeros(size, dtype=tdt, device=device))
+        self.add_persistent('N', 0)
         self.decay = decay
         self.eps = eps
         self._device = device

@@ -289,6 +289,30 @@ def main():
                                    rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(bn.avg_var.cpu().numpy(), z['mn|%d|avg_var' % rank],
                                    rtol=1e-4, atol=1e-6)
+    # ---- AllreducePersistent: running statistics become their mean over the ranks ----
+    from chainer_b200.core import link as L
+    from chainer_b200.extensions import AllreducePersistent
+
+    class _Net(L.Chain):
+        def __init__(self):
+            super(_Net, self).__init__()
+            with self.init_scope():
+                self.bn1 = MultiNodeBatchNormalization(64, comm)
+                self.bn2 = MultiNodeBatchNormalization(5, comm)
+
+    net = _Net()
+    net.bn1.avg_mean.fill_(float(rank))
+    net.bn1.avg_var.copy_(torch.arange(64, device='cuda', dtype=torch.float32) * (rank + 1))
+    net.bn2.avg_mean.fill_(1.5)
+    net.bn1.N = 3 + rank
+    AllreducePersistent(net, comm)()
+    torch.cuda.synchronize()
+    mr = (world - 1) / 2.0
+    np.testing.assert_allclose(net.bn1.avg_mean.cpu().numpy(), np.full(64, mr), rtol=1e-6)
+    np.testing.assert_allclose(net.bn1.avg_var.cpu().numpy(), np.arange(64) * (mr + 1), rtol=1e-6)
+    np.testing.assert_allclose(net.bn2.avg_mean.cpu().numpy(), np.full(5, 1.5), rtol=1e-6)
+    assert net.bn1.N == 3 + rank
+
     if os.environ.get('CHAINER_B200_MULTICAST') == '1' and comm._p2p is not None \
             and comm._p2p.multicast_supported:
         assert comm._mc_active(comm.gpu_buffer_a), 'the public API should have used the multicast path'

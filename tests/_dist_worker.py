@@ -100,6 +100,72 @@ def main():
             np.testing.assert_allclose(p.grad, g, rtol=1e-6, atol=1e-9)
         assert actual.t == step + 1
 
+    # ---- fused GradientClipping + WeightDecay across ranks: the norm is that of the
+    #      MEAN gradient, every rank derives the same rate ----
+    from chainer_b200 import optimizer_hooks as H
+    from chainer_b200.core.link import link_from_named_arrays
+    shapes2 = [(300,), (17, 5), (2048,)]
+    rng2 = np.random.default_rng(3)
+    host_p = [(rng2.standard_normal(s) * 0.05).astype(np.float32) for s in shapes2]
+    net2 = link_from_named_arrays([('/q%d' % i, a.copy()) for i, a in enumerate(host_p)])
+    actual2 = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9)
+    opt2 = chainer_b200.create_multi_node_optimizer(actual2, comm)
+    opt2.setup(net2)
+    opt2.add_hook(H.GradientClipping(0.02))
+    opt2.add_hook(H.WeightDecay(0.01))
+    opt2.update()
+    vs2 = [np.zeros_like(a) for a in host_p]
+    for step in range(2):
+        all_g = [[(np.random.default_rng(500 * (step + 1) + r).standard_normal(s) * 1e-2)
+                  .astype(np.float32) for s in shapes2] for r in range(size)]
+        for (_, p), g in zip(sorted(net2.namedparams()), all_g[rank]):
+            p.grad = g.copy()
+        fake.calls[:] = []
+        opt2.update()
+        names = [c[0] for c in fake.calls]
+        assert names.count('gp_sqnorm') == 1 and 'gp_unpack_momentum_sgd_hooked' in names
+        assert names.index('gp_sqnorm') > max(i for i, n in enumerate(names) if n == 'gp_nccl_allreduce')
+        mean = og.multi_node_mean_grad(all_g, np.float32)
+        rate = og.gradient_clipping_hook(mean, 0.02)
+        assert rate < 1
+        for (_, p), q, v, g in zip(sorted(net2.namedparams()), host_p, vs2, mean):
+            og.weight_decay_hook(q, g, 0.01)
+            og.momentum_sgd_update(q, g, v, 0.01, 0.9)
+            np.testing.assert_allclose(p.data, q, rtol=2e-6, atol=1e-8)
+            np.testing.assert_allclose(p.grad, g, rtol=2e-6, atol=1e-9)
+
+    # ---- AllreducePersistent (chainermn/extensions/allreduce_persistent.py): float
+    #      persistents become their mean over ranks, integers are left alone ----
+    from chainer_b200.core import link as L
+    from chainer_b200.extensions import AllreducePersistent
+
+    class FakeBN(L.Link):
+        def __init__(self, c, dtype):
+            super(FakeBN, self).__init__()
+            self.add_persistent('avg_mean', np.full((c,), rank + 1, dtype=dtype))
+            self.add_persistent('avg_var', np.arange(c, dtype=dtype) * (rank + 1))
+            self.add_persistent('N', 7 + rank)
+
+    class Net(L.Chain):
+        def __init__(self):
+            super(Net, self).__init__()
+            with self.init_scope():
+                self.bn1 = FakeBN(5, np.float32)
+                self.bn2 = FakeBN(3, np.float16)
+                self.bn3 = FakeBN(4, np.float64)
+
+    net3 = Net()
+    fake.calls[:] = []
+    AllreducePersistent(net3, comm)()
+    names = [c[0] for c in fake.calls]
+    assert names.count('gp_nccl_allreduce') == 2          # one per buffer dtype, not per array
+    mean_rank = (size + 1) / 2.0
+    for bn, c in ((net3.bn1, 5), (net3.bn2, 3), (net3.bn3, 4)):
+        np.testing.assert_allclose(bn.avg_mean, np.full((c,), mean_rank), rtol=1e-3)
+        np.testing.assert_allclose(bn.avg_var, np.arange(c) * mean_rank, rtol=1e-3)
+        assert bn.N == 7 + rank
+    assert net3.bn2.avg_mean.dtype == np.float16 and net3.bn3.avg_var.dtype == np.float64
+
     comm.finalize()
     print('RANK %d OK' % rank, flush=True)
 

@@ -318,3 +318,41 @@ def test_standalone_multi_tensor_update_on_gpu(opt_name):
                 og.adam_update_gpu(q, g, s['m'], s['v'], step)
             assert_bits_equal(p.data.cpu().numpy(), q, name)
             assert p.update_rule.t == step
+
+
+def test_allreduce_persistent_on_gpu(comm):
+    """AllreducePersistent over a model with MultiNodeBatchNormalization links: one
+    packed allreduce per buffer dtype; with one worker the mean is the identity,
+    bit-for-bit, and the integer persistent N is left alone."""
+    import torch
+    from chainer_b200 import _lib
+    from chainer_b200.core import link as L
+    from chainer_b200.extensions import AllreducePersistent
+    from chainer_b200.links.batch_normalization import MultiNodeBatchNormalization
+
+    class Net(L.Chain):
+        def __init__(self):
+            super(Net, self).__init__()
+            with self.init_scope():
+                self.bn1 = MultiNodeBatchNormalization(64, comm)
+                self.bn2 = MultiNodeBatchNormalization(1000, comm)
+                self.bn3 = MultiNodeBatchNormalization(7, comm, dtype=np.float16)
+
+    net = Net()
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    want = {}
+    for name, bn in (('bn1', net.bn1), ('bn2', net.bn2), ('bn3', net.bn3)):
+        for attr in ('avg_mean', 'avg_var'):
+            t = getattr(bn, attr)
+            t.copy_(torch.randn(t.shape, device='cuda', generator=gen).to(t.dtype))
+            want[name, attr] = t.clone()
+        bn.N = 11
+    assert sorted(n for n, _ in net.namedlinks()) == ['/', '/bn1', '/bn2', '/bn3']
+    lib = _lib.get()
+    before = lib.launches
+    AllreducePersistent(net, comm)()
+    torch.cuda.synchronize()
+    assert lib.launches - before <= 4            # pack, scale, unpack (+ nothing per array)
+    for (name, attr), t in want.items():
+        assert torch.equal(getattr(getattr(net, name), attr), t), (name, attr)
+    assert net.bn1.N == 11
