@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(1024) p2p_small_kernel(const SmallArgs a) {
     const uint32_t* f = a.flags[a.rank] + threadIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
-      if (clock64() - t0 > 4000000000LL) __trap();
+      if (clock64() - t0 > 20000000000LL) __trap();
     }
   }
   __syncthreads();

@@ -48,8 +48,8 @@ __device__ __forceinline__ void wait_all(const P2PArgs& a, int which, uint32_t v
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(f) - value) < 0) {
       // a peer that never arrives (crashed process) must not hang the GPU:
-      // give up after ~4e9 cycles (about 2 s) with a launch failure
-      if (clock64() - t0 > 4000000000LL) __trap();
+      // give up after ~2e10 cycles (about 10 s) with a launch failure
+      if (clock64() - t0 > 20000000000LL) __trap();
     }
   }
 }
