@@ -184,19 +184,42 @@ class UpdateRule(object):
         # ``optimizer.py:252-305`` without the ChainerX branches
         is_initialized = param.data is not None
         loss_scale = getattr(param, '_loss_scale', None)
+        fp32_converted = False
+        param_ = param
         if self._use_fp32_update and is_initialized and param.dtype == np.float16:
-            raise NotImplementedError(
-                'use_fp32_update for float16 parameters is not implemented on this path yet')
+            # fp32 master weights (``optimizer.py:262-282``): the update runs on a
+            # float32 copy of the parameter with the gradient up-cast to float32
+            from chainer_b200.core import link as _link
+            from chainer_b200.core.optimizers import _single
+            if self._fp32_param is None:
+                master = _single.new_like(param.data, np.float32)
+                _single.cast_copy(master, param.data)
+                self._fp32_param = _link.Parameter(master, name=param.name)
+            fp32_param = self._fp32_param
+            if param.grad is not None:
+                g32 = _single.new_like(param.grad, np.float32)
+                _single.cast_copy(g32, param.grad)
+                fp32_param.grad = g32
+            else:
+                fp32_param.grad = None
+            param_ = fp32_param
+            fp32_converted = True
         if is_initialized:
-            self._init_states(param)
-            if loss_scale is not None and param.grad is not None:
+            self._init_states(param_)
+            if loss_scale is not None and param_.grad is not None:
                 from chainer_b200 import _lib
-                g = param.grad
+                g = param_.grad
                 _lib.get().gp_divide(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
                                      _dev.array_size(g), float(loss_scale), 0)
-        self._hookable.call_hooks('pre', (self, param))
-        self.update_core(param)
-        self._hookable.call_hooks('post', (self, param))
+        self._hookable.call_hooks('pre', (self, param_))
+        self.update_core(param_)
+        self._hookable.call_hooks('post', (self, param_))
+        if fp32_converted:
+            # ``optimizer.py:297-305``: back to the parameter's dtype (written in place:
+            # same values as the reference's ``param.array = fp32.astype(float16)``)
+            from chainer_b200.core.optimizers import _single
+            _single.cast_copy(param.data, param_.data)
+            param_.grad = None
 
     def update_core(self, param):
         self.update_core_gpu(param)

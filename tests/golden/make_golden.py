@@ -11,6 +11,7 @@ Outputs (committed):
   naive_mean_grad.npz   chainermn NaiveCommunicator.multi_node_mean_grad, 2 and 3 ranks
   mnbn.npz              MultiNodeBatchNormalization (_MpiImpl) forward/backward, 2 ranks
   sgd_family.npz        SGD, CorrectedMomentumSGD, NesterovAG (+ hooks), f16/f32/f64
+  fp32_update.npz       float16 parameters with fp32 master weights (use_fp32_update)
   dynamic_loss_scale.npz  MomentumSGD with dynamic loss scaling and a non-finite gradient
   hooks.npz             MomentumSGD / Adam with WeightDecay, GradientClipping hooks and static
                         loss scaling, f16/f32
@@ -193,6 +194,49 @@ def make_sgd_family():
     print('sgd_family', len(out))
 
 
+def make_fp32_update():
+    """float16 parameters with fp32 master weights (use_fp32_update,
+    chainer/optimizer.py:262-305): MomentumSGD, MomentumSGD + WeightDecay + loss scale 128,
+    Adam.  Records the float16 parameters, the float32 masters and states."""
+    from chainer import optimizer_hooks as H
+    out = {}
+    cases = {
+        'sgd': (lambda: optimizers.MomentumSGD(lr=0.01, momentum=0.9), [], None, 1e-2),
+        'sgd_wd_ls128': (lambda: optimizers.MomentumSGD(lr=0.01, momentum=0.9),
+                         [H.WeightDecay(0.05)], 128.0, 1e-2),
+        'adam': (lambda: optimizers.Adam(), [], None, 0.5),
+    }
+    dt = np.dtype('float16')
+    for case, (mk, hooks, ls, gs) in cases.items():
+        rng = np.random.default_rng(31)
+        net = _Net(SHAPES, dt, rng)
+        opt = mk()
+        opt.use_fp32_update()
+        opt.setup(net)
+        for h in hooks:
+            opt.add_hook(h)
+        for n, p in sorted(net.namedparams()):
+            out['%s|init%s' % (case, n)] = p.data.copy()
+        for step in range(3):
+            for n, p in sorted(net.namedparams()):
+                g = np.asarray(rng.standard_normal(p.shape) * gs).astype(dt).reshape(p.shape)
+                if ls is not None:
+                    g = np.asarray(g * dt.type(ls)).astype(dt).reshape(p.shape)
+                    p._loss_scale = ls
+                p.grad = g
+                out['%s|grad%d%s' % (case, step, n)] = g.copy()
+            opt.update()
+            for n, p in sorted(net.namedparams()):
+                assert p.data.dtype == np.float16
+                out['%s|param%d%s' % (case, step, n)] = p.data.copy()
+                out['%s|master%d%s' % (case, step, n)] = p.update_rule._fp32_param.data.copy()
+                for k, st in p.update_rule.state.items():
+                    assert st.dtype == np.float32
+                    out['%s|state_%s%d%s' % (case, k, step, n)] = np.array(st, copy=True)
+    np.savez_compressed(os.path.join(HERE, 'fp32_update.npz'), **out)
+    print('fp32_update', len(out))
+
+
 def make_dynamic_loss_scale():
     """MomentumSGD with dynamic loss scaling (chainer/optimizer.py:736-791, 881-894): 6
     steps, a non-finite gradient in step 2; records the loss scale and the parameters."""
@@ -364,3 +408,4 @@ if __name__ == '__main__':
     make_hooks()
     make_sgd_family()
     make_dynamic_loss_scale()
+    make_fp32_update()

@@ -158,3 +158,54 @@ def run_dynamic_loss_scale(dtype, multi_node, to_arr, to_np):
     np.testing.assert_array_equal(np.asarray(ts), z[pre + 't'])
     if comm is not None:
         comm.finalize()
+
+
+def run_fp32_update(case, multi_node, to_arr, to_np):
+    """fp32_update.npz: float16 parameters updated through float32 master weights."""
+    from tests.test_oracle_golden import FP32_CASES
+    z = _npz('fp32_update.npz')
+    opt_name, wd, ls = FP32_CASES[case]
+    pre = case + '|'
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, to_arr(z[pre + 'init' + n])) for n in names])
+    actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9) if opt_name == 'sgd' \
+        else chainer_b200.Adam()
+    actual.use_fp32_update()
+    comm = None
+    if multi_node:
+        comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=np.float16)
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    else:
+        opt = actual
+    opt.setup(model)
+    if wd is not None:
+        from chainer_b200 import optimizer_hooks as H
+        opt.add_hook(H.WeightDecay(wd))
+    if ls is not None:
+        actual.loss_scaling(scale=ls)
+    if multi_node:
+        opt.update()
+    params = dict(sorted(model.namedparams()))
+    exact = opt_name == 'sgd'           # Adam: GPU formula here, CPU formula in the vectors
+    for step in range(3):
+        for n in names:
+            params[n].grad = to_arr(z[pre + 'grad%d%s' % (step, n)])
+            params[n]._loss_scale = ls
+        opt.update()
+        for n in names:
+            rule = params[n].update_rule
+            want_p, want_m = z[pre + 'param%d%s' % (step, n)], z[pre + 'master%d%s' % (step, n)]
+            got_p = to_np(params[n].data).reshape(want_p.shape)
+            got_m = to_np(rule._fp32_param.data).reshape(want_m.shape)
+            assert got_p.dtype == np.float16 and got_m.dtype == np.float32
+            assert all(to_np(s).dtype == np.float32 for s in rule.state.values())
+            if exact:
+                assert_bits_equal(got_m, want_m, (case, step, n, 'master'))
+                assert_bits_equal(got_p, want_p, (case, step, n))
+            else:
+                np.testing.assert_allclose(got_m, want_m, rtol=2e-5, atol=1e-7)
+                np.testing.assert_allclose(got_p.astype(np.float32), want_p.astype(np.float32),
+                                           rtol=2e-3, atol=1e-6)
+    assert actual.t == 3
+    if comm is not None:
+        comm.finalize()

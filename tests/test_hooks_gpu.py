@@ -310,3 +310,10 @@ def test_clipping_hook_standalone_and_norm_readback():
 def test_dynamic_loss_scaling_gpu(dtype, multi_node):
     from tests.hooks_scenario import run_dynamic_loss_scale
     run_dynamic_loss_scale(dtype, multi_node, lambda a: to_dev(np.array(a)), to_host)
+
+
+@pytest.mark.parametrize('multi_node', [True, False])
+@pytest.mark.parametrize('case', ['sgd', 'sgd_wd_ls128', 'adam'])
+def test_fp32_master_weights_gpu(case, multi_node):
+    from tests.hooks_scenario import run_fp32_update
+    run_fp32_update(case, multi_node, lambda a: to_dev(np.array(a)), to_host)

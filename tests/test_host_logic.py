@@ -638,3 +638,12 @@ def test_dynamic_loss_scaling(fake, dtype, multi_node):
     trajectory, skipped update and parameters bit-for-bit."""
     from tests.hooks_scenario import run_dynamic_loss_scale
     run_dynamic_loss_scale(dtype, multi_node, lambda a: a.copy(), np.asarray)
+
+
+@pytest.mark.parametrize('multi_node', [True, False])
+@pytest.mark.parametrize('case', ['sgd', 'sgd_wd_ls128', 'adam'])
+def test_fp32_master_weights(fake, case, multi_node):
+    """use_fp32_update: float16 parameters, float32 master + states, bit-for-bit the
+    reference for MomentumSGD (also with WeightDecay and loss scaling)."""
+    from tests.hooks_scenario import run_fp32_update
+    run_fp32_update(case, multi_node, lambda a: a.copy(), np.asarray)

@@ -333,3 +333,36 @@ def test_sgd_family_matches_reference(rule, dtype, hooks):
     def check(step, name, what, got, want):
         assert_bits_equal(got, want, (rule, dtype, step, name, what))
     replay_family(_npz('sgd_family.npz'), rule, dtype, hooks, check)
+
+
+# ------------------------------------------------------ fp32 master weights --
+FP32_CASES = {'sgd': ('sgd', None, None), 'sgd_wd_ls128': ('sgd', 0.05, 128.0), 'adam': ('adam', None, None)}
+
+
+@pytest.mark.parametrize('case', sorted(FP32_CASES))
+def test_fp32_update_matches_reference(case):
+    """use_fp32_update (chainer/optimizer.py:262-305) restated with the oracle's pieces:
+    float32 master created once, gradient up-cast, hooks on the float16 gradient first,
+    loss-scale division on the float32 gradient, update in float32, cast back."""
+    z = _npz('fp32_update.npz')
+    opt_name, wd, ls = FP32_CASES[case]
+    pre = case + '|'
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    params = [z[pre + 'init' + n].copy() for n in names]
+    masters = [p.astype(np.float32) for p in params]
+    st = [dict(m=np.zeros_like(q), v=np.zeros_like(q)) for q in masters]
+    for step in range(3):
+        for i, n in enumerate(names):
+            g = z[pre + 'grad%d%s' % (step, n)].copy()
+            if wd is not None:
+                og.weight_decay_hook(params[i], g, wd, ls)          # float16, optimizer-level
+            g32 = g.astype(np.float32)
+            if ls is not None:
+                og.loss_scale_divide(g32, ls)
+            if opt_name == 'sgd':
+                og.momentum_sgd_update(masters[i], g32, st[i]['v'])
+            else:
+                og.adam_update_cpu(masters[i], g32, st[i]['m'], st[i]['v'], step + 1)
+            params[i] = masters[i].astype(np.float16)
+            assert_bits_equal(masters[i], z[pre + 'master%d%s' % (step, n)], (case, step, n, 'master'))
+            assert_bits_equal(params[i], z[pre + 'param%d%s' % (step, n)], (case, step, n))
