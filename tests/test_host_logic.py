@@ -647,3 +647,64 @@ def test_fp32_master_weights(fake, case, multi_node):
     reference for MomentumSGD (also with WeightDecay and loss scaling)."""
     from tests.hooks_scenario import run_fp32_update
     run_fp32_update(case, multi_node, lambda a: a.copy(), np.asarray)
+
+
+def test_hook_changes_and_mixed_loss_scales_switch_paths(fake):
+    """Adding / removing hooks rebuilds the fused plan (hooked <-> plain kernel);
+    parameters that carry DIFFERENT loss scales run the reference sequence; all-zero
+    gradients clip with rate 1 (no NaN from 0/0)."""
+    from chainer_b200 import optimizer_hooks as H
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values()
+    ref = _model_with_values()
+    actual = chainer_b200.MomentumSGD(lr=0.1, momentum=0.9)
+    opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    opt.setup(model)
+    opt.update()                                           # broadcast
+    vs = {n: np.zeros_like(q.data) for n, q in sorted(ref.namedparams()) if q.data is not None}
+
+    def step(seed, expect, decay=None, scales=None, zero=False):
+        _set_grads(model, seed)
+        _set_grads(ref, seed)
+        if zero:
+            for m in (model, ref):
+                for p in m.params():
+                    if p.grad is not None:
+                        p.grad[...] = 0
+        for i, p in enumerate(p for p in model.params() if p.data is not None):
+            p._loss_scale = None if scales is None else scales[i % len(scales)]
+        fake.calls[:] = []
+        opt.update()
+        called = [c[0] for c in fake.calls]
+        assert expect in called, called
+        for i, ((name, p), (_, q)) in enumerate(zip(sorted(model.namedparams()),
+                                                   sorted(ref.namedparams()))):
+            if p.data is None:
+                continue
+            g = q.grad
+            if decay is not None:
+                og.weight_decay_hook(q.data, g, decay, None if scales is None else
+                                     scales[[n for n, r in sorted(ref.namedparams())
+                                             if r.data is not None].index(name) % len(scales)])
+            if scales is not None:
+                og.loss_scale_divide(g, scales[[n for n, r in sorted(ref.namedparams())
+                                                if r.data is not None].index(name) % len(scales)])
+            og.momentum_sgd_update(q.data, g, vs[name], 0.1, 0.9)
+            assert_bits_equal(p.data, q.data, (name, expect))
+        return called
+
+    step(1, 'gp_unpack_momentum_sgd')
+    opt.add_hook(H.WeightDecay(0.01))
+    step(2, 'gp_unpack_momentum_sgd_hooked', decay=0.01)
+    # different loss scales on different parameters: per-parameter reference sequence
+    called = step(3, 'gp_weight_decay', decay=0.01, scales=[2.0, 4.0])
+    assert 'gp_unpack_momentum_sgd_hooked' not in called and 'gp_divide' in called
+    step(4, 'gp_unpack_momentum_sgd_hooked', decay=0.01, scales=[8.0])
+    opt.remove_hook('WeightDecay')
+    step(5, 'gp_unpack_momentum_sgd')
+    opt.add_hook(H.GradientClipping(1.0))
+    called = step(6, 'gp_sqnorm', zero=True)
+    assert 'gp_unpack_momentum_sgd_hooked' in called
+    for p in model.params():
+        if p.data is not None:
+            assert np.isfinite(p.data).all() and np.isfinite(p.grad).all()
