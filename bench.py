@@ -44,6 +44,9 @@ def parse_args():
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
     ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
+    ap.add_argument('--zero-embedding-rows', type=float, default=0.0,
+                    help='seq2seq (config 4 variant): fraction of embedding-gradient rows set to zero '
+                         '(token sparsity; values only, layout unchanged)')
     ap.add_argument('--mc-chunk-mb', type=float, default=None, help='multicast path: pipeline chunk size')
     ap.add_argument('--multicast', choices=['auto', 'on', 'off'], default='auto',
                     help='NVSwitch multicast allreduce kernel (auto: 4 and 8 GPUs)')
@@ -270,6 +273,13 @@ def b200_main(args):
     views = lambda arena: [arena[offs[i]:offs[i + 1]] for i in range(len(sizes))]  # noqa: E731
     p_views = views(p_arena)
     g_views = [views(a) for a in g_arenas]
+    if args.zero_embedding_rows > 0:
+        # EmbedID's dense W-gradient has non-zero rows only for the tokens of the batch
+        for gv in g_views:
+            for (nm, shape), g in zip(plist, gv):
+                if 'embed' in nm and len(shape) == 2:
+                    rows = torch.rand(shape[0], device='cuda', generator=gen) < args.zero_embedding_rows
+                    g.view(shape)[rows] = 0
     model = link_from_named_arrays([(nm, v) for (nm, _), v in zip(plist, p_views)])
     params_sorted = [p for _, p in sorted(model.namedparams())]
     actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9) if optimizer_name == 'momentum_sgd' \
@@ -378,6 +388,7 @@ def b200_main(args):
             'api': 'create_multi_node_optimizer(MomentumSGD|Adam, pure_nccl).update()',
             'bucket_bytes': comm.bucket_bytes if world > 1 else None,
             'allreduce_impl': (None if world == 1 else _allreduce_impl(comm)),
+            'zero_embedding_rows': args.zero_embedding_rows or None,
         },
         'roofline': {
             'bound': 'hbm', 'kernel': kern['update_kernel'], 'achieved': achieved, 'peak': peak,
