@@ -35,7 +35,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=20)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker'])
     ap.add_argument('--workload', default='resnet50', choices=['resnet50', 'seq2seq', 'mnist_mlp'])
     ap.add_argument('--optimizer', default=None, choices=[None, 'momentum_sgd', 'adam'])
     ap.add_argument('--allreduce-dtype', default='float32',
@@ -177,6 +177,76 @@ def run_cpu_reference(args, sizes, optimizer_name, budget_s, steps=None, warmup=
     return n / (ms * 1e-3), ms, len(times)
 
 
+def reference_worker_main(args):
+    """One CPU rank of the reference arm at N > 1: the `naive` communicator's step
+    (per-parameter in-place Allreduce over the host cores, here gloo in place of MPI,
+    then `*= 1/size` and update_core_cpu).  Launched by reference_main."""
+    import torch
+    import torch.distributed as dist
+    from oracle import naive
+    torch.set_num_threads(1)
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    plist, sizes = workload_sizes(args.workload)
+    optimizer_name = args.optimizer or default_optimizer(args.workload)
+    rng = np.random.default_rng(7)
+    params = [(rng.standard_normal(k) * 0.05).astype(np.float32) for k in sizes]
+    grng = np.random.default_rng(1000 + rank)
+    grads0 = [(grng.standard_normal(k) * 1e-2).astype(np.float32) for k in sizes]
+    opt = naive.MomentumSGD(params, 0.01, 0.9) if optimizer_name == 'momentum_sgd' \
+        else naive.Adam(params)
+
+    def allreduce(a):
+        if a.size:
+            dist.all_reduce(torch.from_numpy(a))          # in place, like MPI.IN_PLACE
+
+    times = []
+    for i in range(args.warmup + args.steps):
+        grads = [g.copy() for g in grads0]
+        dist.barrier()
+        t0 = time.perf_counter()
+        naive.step(params, grads, opt, size=world, allreduce=allreduce)
+        dist.barrier()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    if rank == 0:
+        print('CPU_REFERENCE_RESULT ' + json.dumps({'ms': 1e3 * float(np.median(times)),
+                                                    'steps': len(times)}), flush=True)
+    dist.destroy_process_group()
+
+
+def run_cpu_reference_ranks(args, n_ranks, steps, warmup):
+    """N CPU ranks of the reference's naive path on this box's host cores (what
+    `mpiexec -n N` with the `naive` communicator runs); returns (ms/step, steps)."""
+    import socket
+    import subprocess
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(n_ranks):
+        env = {k: v for k, v in os.environ.items() if not k.startswith('TORCHELASTIC')}
+        env.update(RANK=str(r), WORLD_SIZE=str(n_ranks), LOCAL_RANK=str(r),
+                   MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), OMP_NUM_THREADS='1',
+                   CUDA_VISIBLE_DEVICES='')
+        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference-worker',
+               '--gpus', str(n_ranks), '--steps', str(steps), '--warmup', str(warmup),
+               '--workload', args.workload]
+        if args.optimizer:
+            cmd += ['--optimizer', args.optimizer]
+        procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=1500)[0] for p in procs]
+    if any(p.returncode != 0 for p in procs):
+        raise RuntimeError('CPU reference ranks failed:\n' + '\n'.join(o[-2000:] for o in outs))
+    for line in outs[0].splitlines():
+        if line.startswith('CPU_REFERENCE_RESULT '):
+            res = json.loads(line[len('CPU_REFERENCE_RESULT '):])
+            return res['ms'], res['steps']
+    raise RuntimeError('CPU reference rank 0 printed no result:\n' + outs[0][-2000:])
+
+
 def reference_main(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -184,25 +254,35 @@ def reference_main(args):
     plist, sizes = workload_sizes(args.workload)
     optimizer_name = args.optimizer or default_optimizer(args.workload)
     pack_b, upd_b = bytes_per_elem(optimizer_name, 4, True)
-    steps = max(1, min(args.steps, 50))
-    eps, ms, done = run_cpu_reference(args, sizes, optimizer_name, args.cpu_seconds, steps=steps,
-                                      warmup=max(1, min(args.warmup, 3)))
     n = sum(sizes)
+    n_ranks = max(1, args.gpus)
+    if n_ranks == 1:
+        steps = max(1, min(args.steps, 50))
+        eps, ms, done = run_cpu_reference(args, sizes, optimizer_name, args.cpu_seconds,
+                                          steps=steps, warmup=max(1, min(args.warmup, 3)))
+    else:
+        # the reference's CPU job of the same shape: N ranks of the naive communicator
+        ms, done = run_cpu_reference_ranks(args, n_ranks, steps=max(1, min(args.steps, 20)),
+                                           warmup=max(1, min(args.warmup, 2)))
+        eps = n_ranks * n / (ms * 1e-3)
     gbs = eps * (pack_b + upd_b) / 1e9
-    sample = '{} steps of the full {} workload ({} tensors, {} elements), 1 rank'.format(
-        done, args.workload, len(sizes), n)
+    sample = '{} steps of the full {} workload ({} tensors, {} elements), {} rank{}'.format(
+        done, args.workload, len(sizes), n, n_ranks,
+        '' if n_ranks == 1 else 's (one process each, gloo allreduce per parameter)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': gbs, 'unit': 'GB/s', 'n_gpus': args.gpus,
         'steps': done, 'warmup': max(1, min(args.warmup, 3)), 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': workload_name(args, optimizer_name, 1), 'n_tensors': len(sizes),
+        'config': {'workload': workload_name(args, optimizer_name, n_ranks), 'n_tensors': len(sizes),
                    'n_elems': n, 'bytes_per_elem': pack_b + upd_b},
-        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
+        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': n_ranks, 'kind': 'port',
                          'sample': sample, 'host_cores': os.cpu_count()},
         'e2e': {'value': gbs, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'NumPy port (oracle/naive.py) of the reference naive communicator + '
-                'update_core_cpu; the reference NumPy path is single-threaded per process',
+                'update_core_cpu; the reference NumPy path is single-threaded per process, so '
+                'the job uses one host core per rank (N ranks at --gpus N, gloo standing in '
+                'for MPI)',
     }
     print(json.dumps(line), flush=True)
 
@@ -577,6 +657,8 @@ def main():
     args = parse_args()
     if args.impl == 'reference':
         reference_main(args)
+    elif args.impl == 'reference-worker':
+        reference_worker_main(args)
     else:
         b200_main(args)
 
