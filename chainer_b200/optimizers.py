@@ -1,188 +1,170 @@
-"""Multi-node optimizer wrappers: mirror of ``chainermn/optimizers.py:5-182``.
+"""Multi-node optimizer wrappers behind ``create_multi_node_optimizer``.
 
-``_MultiNodeOptimizer.update`` keeps the reference protocol -- forward /
-backward, then ``bcast_data`` on the first call or after the parameter set
-changed (and NO update on that call), else mean-gradient + update -- but asks
-the communicator for the fused pipeline first
-(``PureNcclCommunicator.multi_node_mean_grad_and_update``); when that declines
-(hooks, loss scaling, custom rules ...) the two reference steps run unfused.
+Behavioural mirror of ``chainermn/optimizers.py:5-182`` (same public names,
+same protocol, same attribute forwarding), organised around one proxy base:
+
+* ``update(lossfun=None, ...)`` runs forward / backward when a loss function is
+  given, then EITHER broadcasts the parameters (first call, or the parameter set
+  changed -- and performs NO update on that call, ``:29-30``) OR averages the
+  gradients over the workers and updates (``:31-33``).
+* The plain wrapper first offers the step to the communicator's fused pipeline
+  (``PureNcclCommunicator.multi_node_mean_grad_and_update``: pack -> allreduce ->
+  fused unpack + update); when that declines (custom hooks or rules, dynamic loss
+  scaling ...) the two reference steps run one after the other.
+* The double-buffering wrapper (``:59-146``) averages the gradients of step k on a
+  side stream while step k + 1 computes, and applies them one call late.
+
+Every attribute that is not the wrapper's own is read from / written to the
+wrapped optimizer (``:52-56``), so ``opt.lr = ...``, ``opt.add_hook(...)``,
+``opt.t`` behave as on the optimizer itself.
 """
 import copy
 
 from chainer_b200 import device as _dev
 
 
-class _MultiNodeOptimizer(object):
+def _layout_signature(link):
+    """What `is_changed` compares: the sorted parameter names and whether each
+    parameter is initialised (``chainermn/optimizers.py:35-46``)."""
+    return [(name, param.data is not None) for name, param in sorted(link.namedparams())]
 
-    def __init__(self, actual_optimizer, communicator, zero_fill):
-        super(_MultiNodeOptimizer, self).__setattr__(
-            'communicator', communicator)
-        super(_MultiNodeOptimizer, self).__setattr__(
-            'actual_optimizer', actual_optimizer)
-        super(_MultiNodeOptimizer, self).__setattr__(
-            'target_params', [])
-        super(_MultiNodeOptimizer, self).__setattr__(
-            'zero_fill', zero_fill)
 
-    def update(self, lossfun=None, *args, **kwds):
-        target = self.target
-        if lossfun is not None:
-            use_cleargrads = getattr(self, '_use_cleargrads', True)
-            loss = lossfun(*args, **kwds)
-            if use_cleargrads:
-                target.cleargrads()
-            else:
-                target.zerograds()
-            loss.backward(loss_scale=self.actual_optimizer._loss_scale)
-            del loss
+class _OptimizerProxy(object):
+    """Holds the wrapper's own fields in ``__dict__`` and forwards every other
+    attribute access to ``actual_optimizer``."""
 
-        if self.is_changed(target):
-            self.communicator.bcast_data(target)
-        else:
-            fused = getattr(self.communicator, 'multi_node_mean_grad_and_update', None)
-            if fused is not None and not args and not kwds and \
-                    fused(target, self.actual_optimizer, self.zero_fill):
-                return
-            self.communicator.multi_node_mean_grad(target, self.zero_fill)
-            self.actual_optimizer.update(None, *args, **kwds)
+    def __init__(self, actual_optimizer, communicator, zero_fill, **own):
+        fields = dict(actual_optimizer=actual_optimizer, communicator=communicator,
+                      zero_fill=zero_fill)
+        fields.update(own)
+        for key, value in fields.items():
+            self._own(key, value)
 
-    def is_changed(self, target):
-        # Fast path: Link classes that count structural changes
-        # (chainer_b200.core.link) need not be re-walked every step.
-        if getattr(target, '_b200_versioned', False):
-            from chainer_b200.core import link as _link
-            stamp = (id(target), _link.structure_version())
-            if self.__dict__.get('_stamp') == stamp:
-                return False
-            super(_MultiNodeOptimizer, self).__setattr__('_stamp', stamp)
-        previous_params = self.target_params
-        super(_MultiNodeOptimizer, self).__setattr__(
-            'target_params', [(name, param.data is not None)
-                              for name, param in sorted(target.namedparams())])
-        if len(previous_params) != len(self.target_params):
-            return True
+    def _own(self, name, value):
+        object.__setattr__(self, name, value)
 
-        for param1, param2 in zip(self.target_params, previous_params):
-            if (param1[0] != param2[0]) or param1[1] != param2[1]:
-                return True
-        return False
+    def __getattr__(self, name):
+        # only reached for names that are not the wrapper's own
+        if name == 'actual_optimizer':          # half-built instance (copy / pickle)
+            raise AttributeError(name)
+        return getattr(self.actual_optimizer, name)
+
+    def __setattr__(self, name, value):
+        setattr(self.actual_optimizer, name, value)
 
     def setup(self, link):
         self.actual_optimizer.setup(link)
         return self
 
-    def __getattr__(self, attr_name):
-        return getattr(self.actual_optimizer, attr_name)
+    def _compute_gradients(self, lossfun, args, kwds):
+        """The forward / backward half of ``Optimizer.update(lossfun, ...)``."""
+        if lossfun is None:
+            return
+        target = self.target
+        loss = lossfun(*args, **kwds)
+        if getattr(self, '_use_cleargrads', True):
+            target.cleargrads()
+        else:
+            target.zerograds()
+        loss.backward(loss_scale=self.actual_optimizer._loss_scale)
 
-    def __setattr__(self, attr_name, value):
-        setattr(self.actual_optimizer, attr_name, value)
 
-
-class _DoubleBufferingOptimizer(object):
-    """1-step-stale overlap (``chainermn/optimizers.py:59-146``): gradients are
-    swapped into a deep copy of the model (``communicated_target``), averaged on
-    a non-blocking side stream while the next forward/backward runs, and applied
-    one call late."""
+class _MultiNodeOptimizer(_OptimizerProxy):
 
     def __init__(self, actual_optimizer, communicator, zero_fill):
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'communicator', communicator)
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'actual_optimizer', actual_optimizer)
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'needs_update', False)
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'communicated_target', None)
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'target_params_list', [[], []])
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'allreduce_grad_stream', _dev.Stream(non_blocking=True))
-        super(_DoubleBufferingOptimizer, self).__setattr__(
-            'zero_fill', zero_fill)
+        super(_MultiNodeOptimizer, self).__init__(actual_optimizer, communicator, zero_fill,
+                                                  target_params=[], _stamp=None)
 
     def update(self, lossfun=None, *args, **kwds):
+        self._compute_gradients(lossfun, args, kwds)
         target = self.target
-        if lossfun is not None:
-            use_cleargrads = getattr(self, '_use_cleargrads', True)
-            loss = lossfun(*args, **kwds)
-            if use_cleargrads:
-                target.cleargrads()
-            else:
-                target.zerograds()
-            loss.backward(loss_scale=self.actual_optimizer._loss_scale)
-            del loss
+        comm = self.communicator
+        if self.is_changed(target):
+            comm.bcast_data(target)
+            return
+        if not args and not kwds:
+            fused = getattr(comm, 'multi_node_mean_grad_and_update', None)
+            if fused is not None and fused(target, self.actual_optimizer, self.zero_fill):
+                return
+        comm.multi_node_mean_grad(target, self.zero_fill)
+        self.actual_optimizer.update(None, *args, **kwds)
 
-        if self.is_changed(target, self.target_params_list[0]):
-            self.wait()
+    def is_changed(self, target):
+        """True when the set of (name, initialised?) pairs differs from the one seen
+        at the previous call; remembers the new one."""
+        if getattr(target, '_b200_versioned', False):
+            # Link classes of this package count structural changes: an unchanged
+            # counter means an unchanged layout, without walking the model
+            from chainer_b200.core import link as _link
+            stamp = (id(target), _link.structure_version())
+            if stamp == self._stamp:
+                return False
+            self._own('_stamp', stamp)
+        seen = self.target_params
+        now = _layout_signature(target)
+        self._own('target_params', now)
+        return now != seen
+
+
+class _DoubleBufferingOptimizer(_OptimizerProxy):
+    """One-step-stale overlap: the gradients of the model are swapped into a deep
+    copy (``communicated_target``), averaged there on a non-blocking side stream
+    while the next forward / backward runs, and applied at the next call."""
+
+    def __init__(self, actual_optimizer, communicator, zero_fill):
+        super(_DoubleBufferingOptimizer, self).__init__(
+            actual_optimizer, communicator, zero_fill,
+            needs_update=False, communicated_target=None, target_params_list=[[], []],
+            allreduce_grad_stream=_dev.Stream(non_blocking=True))
+
+    def update(self, lossfun=None, *args, **kwds):
+        self._compute_gradients(lossfun, args, kwds)
+        target = self.target
+        mine, shadow = self.target_params_list
+        changed = self.is_changed(target, mine)
+        self.wait()
+        if changed:
             self.communicator.bcast_data(target)
-            super(_DoubleBufferingOptimizer, self).__setattr__(
-                'communicated_target', copy.deepcopy(target))
-            super(_DoubleBufferingOptimizer, self).__setattr__(
-                'target_params_list', [
-                    list(sorted(self.target.namedparams())),
-                    list(sorted(self.communicated_target.namedparams()))])
-            super(_DoubleBufferingOptimizer, self).__setattr__(
-                'needs_update', False)
+            twin = copy.deepcopy(target)
+            self._own('communicated_target', twin)
+            self._own('target_params_list', [sorted(target.namedparams()),
+                                             sorted(twin.namedparams())])
+            self._own('needs_update', False)
+            return
+        self.swap_grad(mine, shadow)
+        self.multi_node_mean_grad_async()
+        if self.needs_update:
+            # the gradients averaged during the PREVIOUS call are in the model now
+            self.actual_optimizer.update(None, *args, **kwds)
         else:
-            self.wait()
-            self.swap_grad(self.target_params_list[0],
-                           self.target_params_list[1])
-            self.multi_node_mean_grad_async()
-            if self.needs_update:
-                self.actual_optimizer.update(None, *args, **kwds)
-            else:
-                super(_DoubleBufferingOptimizer, self).__setattr__(
-                    'needs_update', True)
+            self._own('needs_update', True)
 
     def multi_node_mean_grad_async(self):
         self.communicator._multi_node_mean_grad_async(
-            self.communicated_target, self.zero_fill,
-            self.allreduce_grad_stream)
+            self.communicated_target, self.zero_fill, self.allreduce_grad_stream)
 
     def is_changed(self, target, previous_params):
-        target_params = list(sorted(target.namedparams()))
-        if len(previous_params) != len(target_params):
-            return True
-
-        for param1, param2 in zip(target_params, previous_params):
-            name1, var1 = param1
-            name2, var2 = param2
-            if (name1 != name2) or (var1.data is None) != (var2.data is None):
-                return True
-        return False
+        before = [(name, p.data is not None) for name, p in previous_params]
+        return _layout_signature(target) != before
 
     def swap_grad(self, target1_params, target2_params):
-        for param1, param2 in zip(target1_params, target2_params):
-            _, var1 = param1
-            _, var2 = param2
-            var1.grad, var2.grad = var2.grad, var1.grad
+        for (_, a), (_, b) in zip(target1_params, target2_params):
+            a.grad, b.grad = b.grad, a.grad
 
     def wait(self):
         self.allreduce_grad_stream.synchronize()
         _dev.Stream.null.synchronize()
 
-    def setup(self, link):
-        self.actual_optimizer.setup(link)
-        return self
-
-    def __getattr__(self, attr_name):
-        return getattr(self.actual_optimizer, attr_name)
-
-    def __setattr__(self, attr_name, value):
-        setattr(self.actual_optimizer, attr_name, value)
-
 
 def create_multi_node_optimizer(actual_optimizer, communicator,
                                 double_buffering=False, zero_fill=True):
-    """Create a multi node optimizer from a Chainer optimizer
-    (``chainermn/optimizers.py:149-182``; same arguments)."""
-    if double_buffering:
-        from chainer_b200.communicators.pure_nccl_communicator \
-            import PureNcclCommunicator
-        if not isinstance(communicator, PureNcclCommunicator):
-            raise ValueError(
-                'This communicator does not support double buffering.')
-        return _DoubleBufferingOptimizer(actual_optimizer, communicator,
-                                         zero_fill)
-    return _MultiNodeOptimizer(actual_optimizer, communicator,
-                               zero_fill)
+    """``chainermn.create_multi_node_optimizer`` (``chainermn/optimizers.py:149-182``):
+    wraps ``actual_optimizer`` so that ``update()`` averages gradients over the
+    workers of ``communicator`` first.  ``double_buffering`` needs the ``pure_nccl``
+    communicator; ``zero_fill`` treats missing gradients as zeros in the mean."""
+    if not double_buffering:
+        return _MultiNodeOptimizer(actual_optimizer, communicator, zero_fill)
+    from chainer_b200.communicators.pure_nccl_communicator import PureNcclCommunicator
+    if not isinstance(communicator, PureNcclCommunicator):
+        raise ValueError('This communicator does not support double buffering.')
+    return _DoubleBufferingOptimizer(actual_optimizer, communicator, zero_fill)
