@@ -105,6 +105,14 @@ def _copy_array(a):
     return a.copy()
 
 
+def _assign_array(dst, src):
+    """dst[...] = src for arrays of one module (torch tensors, NumPy arrays)."""
+    if _dev.is_torch(dst):
+        dst.copy_(src)
+    else:
+        dst[...] = src
+
+
 class Link(object):
 
     _b200_versioned = True
@@ -181,6 +189,30 @@ class Link(object):
 
     def children(self):
         return iter(())
+
+    def copyparams(self, link, copy_persistent=True):
+        """``link.py:1008-1040``: copy the parameter values (and persistents) of a link
+        of the same structure into this one, array by array."""
+        src = dict(link.namedparams())
+        for path, p in self.namedparams():
+            q = src[path]
+            if q.data is None:
+                continue
+            if p.data is None:
+                p.data = _copy_array(q.data)
+            else:
+                _assign_array(p.data, q.data)
+        if copy_persistent:
+            mine = dict(self.namedlinks())
+            for path, other in link.namedlinks():
+                dst = mine[path]
+                for name in other._persistent:
+                    value = other.__dict__[name]
+                    cur = dst.__dict__.get(name)
+                    if hasattr(value, 'dtype') and cur is not None and hasattr(cur, 'dtype'):
+                        _assign_array(cur, value)
+                    else:
+                        dst.add_persistent(name, copy.deepcopy(value))
 
     def cleargrads(self):
         for p in self.params():

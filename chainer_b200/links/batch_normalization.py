@@ -76,7 +76,15 @@ class MultiNodeBatchNormalization(link.Link):
                  initial_gamma=None, initial_beta=None,
                  communication_backend='auto', device='cuda'):
         super(MultiNodeBatchNormalization, self).__init__()
+        backend = mnbn_functions.get_communication_backend(comm, communication_backend)
+        self._setup(size, comm, backend, decay, eps, dtype, use_gamma, use_beta,
+                    initial_gamma, initial_beta, device)
+
+    def _setup(self, size, comm, backend, decay, eps, dtype, use_gamma, use_beta,
+               initial_gamma, initial_beta, device):
         torch = _torch()
+        if isinstance(size, (tuple, list)):
+            size, = size
         self._highprec_dtype = config.get_dtype(dtype, map_mixed16=np.float32)
         tdt = {np.dtype(np.float16): torch.float16, np.dtype(np.float32): torch.float32,
                np.dtype(np.float64): torch.float64}[np.dtype(self._highprec_dtype)]
@@ -89,8 +97,7 @@ class MultiNodeBatchNormalization(link.Link):
         self.eps = eps
         self._device = device
         self._tdt = tdt
-        self._communication_backend = \
-            mnbn_functions.get_communication_backend(comm, communication_backend)
+        self._communication_backend = backend
         with self.init_scope():
             if use_gamma:
                 g = torch.full((size,), 1.0 if initial_gamma is None else float(initial_gamma),
@@ -100,6 +107,16 @@ class MultiNodeBatchNormalization(link.Link):
                 b = torch.full((size,), 0.0 if initial_beta is None else float(initial_beta),
                                dtype=tdt, device=device)
                 self.beta = link.Parameter(b)
+
+    def __deepcopy__(self, memo):
+        # a copy of the link shares the communicator (handles of live collectives
+        # cannot be duplicated); parameters and persistents are copied
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for key, value in self.__dict__.items():
+            new.__dict__[key] = value if key == 'comm' else copy.deepcopy(value, memo)
+        return new
 
     def _impl(self):
         return mnbn_functions.MultiNodeBNImplSelector(
@@ -134,3 +151,32 @@ class MultiNodeBatchNormalization(link.Link):
 
     def start_finetuning(self):
         self.N = 0
+
+
+class _SingleWorker(object):
+    """The communicator of a link that normalises over the local batch only (one
+    shared instance: it only carries the statistics kernels' scratch)."""
+    size = 1
+    rank = 0
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+
+_LOCAL = _SingleWorker()
+
+
+class BatchNormalization(MultiNodeBatchNormalization):
+    """Single-worker batch normalisation on the same statistics kernels: the
+    stand-in of ``chainer.links.BatchNormalization`` that ``create_mnbn_model``
+    replaces (``chainermn/links/create_mnbn_model.py:27-41``).  Same parameters and
+    persistents as the multi-node link; statistics over the local batch."""
+
+    def __init__(self, size, decay=0.9, eps=2e-5, dtype=None, use_gamma=True, use_beta=True,
+                 initial_gamma=None, initial_beta=None, device='cuda'):
+        link.Link.__init__(self)
+        self._setup(size, _LOCAL, 'nccl', decay, eps, dtype, use_gamma, use_beta,
+                    initial_gamma, initial_beta, device)

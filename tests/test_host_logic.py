@@ -708,3 +708,83 @@ def test_hook_changes_and_mixed_loss_scales_switch_paths(fake):
     for p in model.params():
         if p.data is not None:
             assert np.isfinite(p.data).all() and np.isfinite(p.grad).all()
+
+
+# ----------------------------------------- BatchNormalization / create_mnbn_model --
+def test_batch_normalization_link_and_create_mnbn_model(fake):
+    """BatchNormalization (single worker) matches torch's batch_norm forward / backward
+    and running statistics; create_mnbn_model returns a structural copy whose BN links
+    are MultiNodeBatchNormalization with the same parameters and persistents
+    (chainermn/links/create_mnbn_model.py:7-66), leaving the original untouched."""
+    import torch
+    from chainer_b200.links import (BatchNormalization, MultiNodeBatchNormalization,
+                                    create_mnbn_model)
+
+    class Block(L.Chain):
+        def __init__(self):
+            super(Block, self).__init__()
+            with self.init_scope():
+                self.bn = BatchNormalization(6, device='cpu')
+                self.fc = Linear(3, 2)
+
+    class Net(L.Chain):
+        def __init__(self):
+            super(Net, self).__init__()
+            with self.init_scope():
+                self.block = Block()
+                self.bn0 = BatchNormalization(4, decay=0.8, eps=1e-3, device='cpu')
+                self.tail = L.ChainList(BatchNormalization(5, use_beta=False, device='cpu'),
+                                        Linear(2, 2))
+
+    torch.manual_seed(0)
+    net = Net()
+    # forward / backward of the single-worker link against torch
+    x = torch.randn(8, 4, 3, 3, requires_grad=True)
+    net.bn0.gamma.data.copy_(torch.rand(4) + 0.5)
+    net.bn0.beta.data.copy_(torch.randn(4))
+    net.bn0.gamma.data.requires_grad_(True)
+    net.bn0.beta.data.requires_grad_(True)
+    y = net.bn0(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2 = x.detach().clone().requires_grad_(True)
+    g2 = net.bn0.gamma.data.detach().clone().requires_grad_(True)
+    b2 = net.bn0.beta.data.detach().clone().requires_grad_(True)
+    rm, rv = torch.zeros(4), torch.zeros(4)
+    y2 = torch.nn.functional.batch_norm(x2, rm, rv, g2, b2, training=True, momentum=0.2, eps=1e-3)
+    y2.backward(gy)
+    np.testing.assert_allclose(y.detach().numpy(), y2.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x.grad.numpy(), x2.grad.numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(net.bn0.gamma.data.grad.numpy(), g2.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(net.bn0.beta.data.grad.numpy(), b2.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(net.bn0.avg_mean.numpy(), rm.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(net.bn0.avg_var.numpy(), rv.numpy(), rtol=1e-4, atol=1e-6)
+    net.bn0.N = 5
+
+    comm = chainer_b200.create_communicator('pure_nccl')
+    twin = create_mnbn_model(net, comm)
+    assert [p for p, _ in twin.namedlinks()] == [p for p, _ in net.namedlinks()]
+    assert [n for n, _ in sorted(twin.namedparams())] == [n for n, _ in sorted(net.namedparams())]
+    for (path, a), (_, b) in zip(net.namedlinks(), twin.namedlinks()):
+        assert a is not b
+        if isinstance(a, BatchNormalization):
+            assert type(b) is MultiNodeBatchNormalization and b.comm is comm
+            assert b.decay == a.decay and b.eps == a.eps and b.N == a.N
+            assert hasattr(b, 'beta') == hasattr(a, 'beta')
+            for attr in ('avg_mean', 'avg_var'):
+                assert getattr(b, attr) is not getattr(a, attr)
+                assert torch.equal(getattr(b, attr), getattr(a, attr))
+        else:
+            assert type(b) is type(a)
+    for (n, p), (_, q) in zip(sorted(net.namedparams()), sorted(twin.namedparams())):
+        assert p is not q and p.data is not q.data
+        np.testing.assert_array_equal(np.asarray(p.data.detach() if hasattr(p.data, 'detach') else p.data),
+                                      np.asarray(q.data.detach() if hasattr(q.data, 'detach') else q.data))
+    # the copy is independent of the original
+    twin.bn0.avg_mean.add_(1.0)
+    assert not torch.equal(twin.bn0.avg_mean, net.bn0.avg_mean)
+    # and computes the same thing with one worker
+    y3 = twin.bn0(x.detach(), train=False)
+    y4 = net.bn0(x.detach(), train=False)
+    assert y3.shape == y4.shape
+    comm.finalize()
