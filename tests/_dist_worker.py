@@ -100,6 +100,38 @@ def main():
             np.testing.assert_allclose(p.grad, g, rtol=1e-6, atol=1e-9)
         assert actual.t == step + 1
 
+    # ---- BASELINE configs[0]: MNIST MLP (784-1000-1000-10, 6 tensors, 1,796,010 elements),
+    #      Adam defaults, gradients ~ N(0, 1e-2) from default_rng(1000 + rank) ----
+    from chainer_b200 import workloads
+    from chainer_b200.core.link import link_from_named_arrays as _from_arrays
+    mlp = workloads.mnist_mlp()
+    assert sum(int(np.prod(sh)) for _, sh in mlp) == 1796010 and len(mlp) == 6
+    prng = np.random.default_rng(7)
+    mlp_p = [(prng.standard_normal(sh) * 0.05).astype(np.float32) for _, sh in mlp]
+    mlp_net = _from_arrays([(nm, a.copy()) for (nm, _), a in zip(mlp, mlp_p)])
+    adam = chainer_b200.Adam()
+    mlp_opt = chainer_b200.create_multi_node_optimizer(adam, comm)
+    mlp_opt.setup(mlp_net)
+    comm.bucket_bytes = 256 << 20
+    mlp_opt.update()
+    mlp_st = [dict(m=np.zeros_like(a), v=np.zeros_like(a)) for a in mlp_p]
+    for step in range(1, 4):
+        all_g = [[(np.random.default_rng(1000 + r + 10 * step).standard_normal(sh) * 1e-2)
+                  .astype(np.float32) for _, sh in mlp] for r in range(size)]
+        for (_, p), g in zip(sorted(mlp_net.namedparams()), all_g[rank]):
+            p.grad = g.copy()
+        mlp_opt.update()
+        mean = og.multi_node_mean_grad(all_g, np.float32)
+        for (_, p), q, g, st in zip(sorted(mlp_net.namedparams()), mlp_p, mean, mlp_st):
+            og.adam_update_gpu(q, g, st['m'], st['v'], step)
+            np.testing.assert_allclose(p.grad, g, rtol=1e-6, atol=1e-9)
+            # 3 ranks: gloo's summation order differs from the oracle's rank order by an
+            # ulp of the mean; Adam divides by sqrt(v) + eps, so the few elements with
+            # |g| ~ eps amplify that (d step / d g ~ alpha / eps).  The mean is judged
+            # strictly above, the step with the amplified bound.
+            np.testing.assert_allclose(p.data, q, rtol=1e-6, atol=2e-7 if size == 2 else 2e-4)
+    assert adam.t == 3
+
     # ---- fused GradientClipping + WeightDecay across ranks: the norm is that of the
     #      MEAN gradient, every rank derives the same rate ----
     from chainer_b200 import optimizer_hooks as H
