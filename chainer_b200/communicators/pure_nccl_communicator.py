@@ -26,6 +26,7 @@ What changes underneath (none of it observable through that surface):
 """
 import collections
 import ctypes
+import operator
 import warnings
 
 import numpy as np
@@ -486,10 +487,21 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         self._fused_plan = None
 
 
-def _versions():
+def _version_cells():
     from chainer_b200.core import link as _link
     from chainer_b200.core import optimizer as _opt
-    return (_link.structure_version(), _opt.rules_version())
+    return _link._structure_version, _opt._rules_version
+
+
+_cells = []
+
+
+def _versions():
+    """(structure version, rules version) of chainer_b200.core -- what a cached plan
+    is valid for."""
+    if not _cells:
+        _cells.extend(_version_cells())
+    return (_cells[0][0], _cells[1][0])
 
 
 class _FusedPlan(object):
@@ -575,19 +587,19 @@ class _FusedPlan(object):
         validates new arrays like ParamsData does and uploads one table.
         """
         params = self.params
-        grads = [p.grad for p in params]
-        ids = tuple(map(id, grads))
+        # the gradients are held by their parameters, so the ids are those of live objects
+        ids = tuple(map(id, map(_GET_GRAD, params)))
         if _NONE_ID in ids:
-            for i, g in enumerate(grads):
-                if g is None:
-                    g = _dev.zeros_like(params[i].data)      # zero_fill
-                    params[i].grad = g
-                    grads[i] = g
-            ids = tuple(map(id, grads))
+            for p in params:
+                if p.grad is None:
+                    p.grad = _dev.zeros_like(p.data)         # zero_fill
+            ids = tuple(map(id, map(_GET_GRAD, params)))
         ent = self.cache.get(ids)
         if ent is not None:
-            self.cache.move_to_end(ids)
+            if len(self.cache) > 1:
+                self.cache.move_to_end(ids)
             return ent
+        grads = [p.grad for p in params]
         ptrs = []
         for i, g in enumerate(grads):
             dt = _dev.array_dtype(g)
@@ -724,6 +736,7 @@ class _PlanStale(Exception):
 
 
 _NONE_ID = id(None)
+_GET_GRAD = operator.attrgetter('grad')
 
 
 class _TableSet(object):

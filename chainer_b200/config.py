@@ -12,25 +12,28 @@ When the real ``chainer`` package is importable its functions are used, so that
 ``chainer.using_config('dtype', ...)`` and ``chainer.set_debug`` keep working.
 """
 import os
+import sys
 
 import numpy as np
 
 mixed16 = 'mixed16'
 _debug = [os.environ.get('CHAINER_DEBUG', '0') not in ('0', '')]
 _dtype = [None]
+# read once at import, like chainer.global_config.dtype (chainer/__init__.py:217-218)
+_env_dtype = os.environ.get('CHAINER_DTYPE', 'float32')
+_modules = sys.modules
 
 
 def _real_chainer():
-    import sys
-    return sys.modules.get('chainer')
+    return _modules.get('chainer')
 
 
 def get_dtype(dtype=None, map_mixed16=None):
-    ch = _real_chainer()
+    ch = _modules.get('chainer')
     if ch is not None and hasattr(ch, 'get_dtype'):
         return ch.get_dtype(dtype, map_mixed16)
     if dtype is None:
-        dtype = _dtype[0] if _dtype[0] is not None else os.environ.get('CHAINER_DTYPE', 'float32')
+        dtype = _dtype[0] if _dtype[0] is not None else _env_dtype
     if isinstance(dtype, str) and dtype == mixed16:
         dtype = np.float16 if map_mixed16 is None else map_mixed16
     return np.dtype(dtype)
