@@ -2,8 +2,10 @@
 
 This package is a NumPy restatement of the reference's algorithm for the hot
 path (chainer/chainer v7.8.1): pack/unpack layout, allreduce-mean, MomentumSGD /
-Adam updates, MultiNodeBatchNormalization statistics, and the CPU `naive`
-communicator + NumPy update that serves as the reported CPU baseline.
+Adam (and SGD / CorrectedMomentumSGD / NesterovAG) updates, the WeightDecay /
+GradientClipping hooks and loss scaling, MultiNodeBatchNormalization statistics,
+and the CPU `naive` communicator + NumPy update that serves as the reported CPU
+baseline.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 / ``--impl reference`` legs may import it; the product package ``chainer_b200``
@@ -20,7 +22,10 @@ pinned instead against
     (MomentumSGDRule / AdamRule ``update_core_cpu``, NaiveCommunicator
     ``multi_node_mean_grad`` through an mpi4py stand-in,
     GeneralBatchNormalizationImpl + ``_MpiImpl`` statistics,
-    ``sorted(model.namedparams())`` layouts of the example models); the
+    ``sorted(model.namedparams())`` layouts of the example models, the
+    ``WeightDecay`` / ``GradientClipping`` hooks with static loss scaling, SGD /
+    CorrectedMomentumSGD / NesterovAG, ``use_fp32_update`` master weights and the
+    dynamic loss-scale schedule -- all reproduced bit for bit); the
     generated vectors are committed under ``tests/golden/`` and checked by
     ``tests/test_oracle_golden.py``;
   * the known-answer tests of the reference's own test-suite
