@@ -6,13 +6,26 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path over one synthetic gradient set of the
-workload: pack+cast -> in-place NCCL allreduce (N > 1) -> fused unpack + 1/N
-scale + optimizer update, through the public API
-(`create_multi_node_optimizer(...).update()`), with parameters, optimizer state
-and gradients resident in HBM.  Default workload: BASELINE configs[1], ResNet-50
-(162 tensors, 25,557,096 elements) fp32 gradients, MomentumSGD.
+workload: pack+cast -> sum over the N ranks -> unpack + 1/N scale + optimizer update,
+through the public API (`create_multi_node_optimizer(...).update()`), with parameters,
+optimizer state and gradients resident in HBM.  Default workload: BASELINE configs[1],
+ResNet-50 (162 tensors, 25,557,096 elements) fp32 gradients, MomentumSGD.
 
-Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+Rank 0 prints ONE JSON line (DESIGN.md "Measurement" explains every key):
+  value / ms_per_step   device-timed whole-job throughput of the step (CUDA events, max over ranks)
+  roofline              the dominant kernel against the measured HBM peak (+ whole-step fractions)
+  parity                J more steps through the same call, replayed by the NumPy oracle on a sample
+                        of tensors with every rank's gradients, + bit-identical replicas across ranks
+  allreduce             (N > 1) bus / wire bandwidth of the stand-alone reduction kernel
+  e2e                   the same step with HOST gradients in and HOST parameters out
+  train                 the "ResNet-50 img/s" half of the metric: torchvision resnet50 fwd/bwd
+                        (batch 32/GPU) handing its .grad arrays to the path by pointer
+  cpu_baseline          the reference's CPU path on this box's host cores (N = 1 only)
+
+`--impl reference` times the reference's own CPU implementation of the same step: the
+UNMODIFIED chainermn `naive` communicator + chainer `update_core_cpu` from
+`baseline/_ref` (kind "reference"), or -- when that install is absent -- the NumPy port
+under `oracle/` (kind "port"); N ranks on N host cores at --gpus N.
 """
 import argparse
 import json
@@ -28,12 +41,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = 'mean_grad+update GB/s (ResNet-50 gradient path; algorithmic HBM bytes / time)'
+NOMINAL_HBM_GBS = 8000.0       # north_star: "~8 TB/s HBM peak"
+NVLINK_GBS = 900.0             # NVLink 5, per direction and GPU
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker'])
     ap.add_argument('--workload', default='resnet50', choices=['resnet50', 'seq2seq', 'mnist_mlp'])
@@ -44,18 +59,28 @@ def parse_args():
                     help='do not keep param.grad observable after the fused update')
     ap.add_argument('--bucket-mb', type=float, default=None)
     ap.add_argument('--no-p2p', action='store_true', help='NCCL allreduce instead of the peer-memory kernel')
+    ap.add_argument('--no-step', action='store_true',
+                    help='separate pack / allreduce / update launches instead of the one-launch step')
     ap.add_argument('--zero-embedding-rows', type=float, default=0.0,
                     help='seq2seq (config 4 variant): fraction of embedding-gradient rows set to zero '
                          '(token sparsity; values only, layout unchanged)')
     ap.add_argument('--mc-chunk-mb', type=float, default=None, help='multicast path: pipeline chunk size')
     ap.add_argument('--multicast', choices=['auto', 'on', 'off'], default='auto',
-                    help='NVSwitch multicast allreduce kernel (auto: 4 and 8 GPUs)')
+                    help='NVSwitch multicast transport (auto: 4 and 8 GPUs)')
     ap.add_argument('--p2p-chunk-mb', type=float, default=None)
     ap.add_argument('--p2p-ctas', type=int, default=None)
+    ap.add_argument('--step-tuning', default='',
+                    help='comma-separated key=value pairs for gp_step_set_tuning')
+    ap.add_argument('--mnbn', action='store_true',
+                    help='add the MultiNodeBatchNormalization statistics leg (BASELINE configs[2])')
     ap.add_argument('--cpu-seconds', type=float, default=10.0,
                     help='budget of the CPU baseline sample')
+    ap.add_argument('--parity-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--reference-kind', default='auto', choices=['auto', 'reference', 'port'])
     return ap.parse_args()
 
 
@@ -66,7 +91,7 @@ def default_optimizer(workload):
 
 
 def bytes_per_elem(optimizer, buf_itemsize, write_grad):
-    """Algorithmic HBM bytes per element (BASELINE.md section 4)."""
+    """Algorithmic HBM bytes per element (SURVEY.md section 8(d))."""
     pack = 4 + buf_itemsize
     if optimizer == 'momentum_sgd':
         upd = buf_itemsize + 8 + 8
@@ -77,19 +102,49 @@ def bytes_per_elem(optimizer, buf_itemsize, write_grad):
     return pack, upd
 
 
+def workload_name(args, optimizer_name, n_gpus):
+    return '{} {} grads, {}, {} (BASELINE configs[{}]) x {} GPU'.format(
+        args.workload, args.allreduce_dtype, optimizer_name, 'pure_nccl',
+        {'resnet50': 1, 'seq2seq': 3, 'mnist_mlp': 0}[args.workload], n_gpus)
+
+
+def _l2_note(working_set):
+    mb = working_set >> 20
+    if mb > 126:
+        return ('inputs larger than L2: working set {} MB per step > 126 MB; gradient arrays rotate '
+                'between 2 sets'.format(mb))
+    return ('working set {} MB per step is below the 126 MB L2 (a latency-bound size): gradient arrays '
+            'rotate between 2 sets, L2 not flushed'.format(mb))
+
+
+def make_config(args, optimizer_name, n_gpus, sizes):
+    """The `config` object: identical for both arms (b200 / reference)."""
+    n = sum(sizes)
+    bsz = 4 if args.allreduce_dtype == 'float32' else 2
+    write_grad = not args.no_write_grad
+    pack_b, upd_b = bytes_per_elem(optimizer_name, bsz, write_grad)
+    return {
+        'workload': workload_name(args, optimizer_name, n_gpus),
+        'n_tensors': len(sizes), 'n_elems': n, 'packed_bytes': n * bsz,
+        'bytes_per_elem': pack_b + upd_b, 'write_grad': write_grad,
+        'optimizer': optimizer_name, 'allreduce_dtype': args.allreduce_dtype,
+        'l2': _l2_note(n * (4 + bsz + 4 + 4 + (4 if optimizer_name == 'adam' else 0))),
+        'zero_embedding_rows': args.zero_embedding_rows or None,
+    }
+
+
 # ------------------------------------------------------------------- clocks --
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the
     benchmark runs (the recipe's nvidia-smi clocks line, in-process so that
     short timed regions are still covered)."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.005):
         super(ClockSampler, self).__init__(daemon=True)
         self.index = index
         self.period = period
         self.samples = []
         self.stop_flag = False
-        self.window = None
         self.ok = False
         try:
             import pynvml
@@ -146,24 +201,87 @@ def workload_sizes(name):
 
 
 # ------------------------------------------------------------ reference arm --
-def run_cpu_reference(args, sizes, optimizer_name, budget_s, steps=None, warmup=1):
-    """The reference's CPU implementation of the path (oracle/naive.py: NumPy port
-    of NaiveCommunicator.multi_node_mean_grad + update_core_cpu), one process,
-    one rank, timed with perf_counter.  Returns (elements/s, ms/step, steps)."""
-    from oracle import naive
-    rng = np.random.default_rng(7)
+def _ref_kind(args):
+    """'reference' when the unmodified chainer/chainermn install is present."""
+    if args.reference_kind != 'auto':
+        return args.reference_kind
+    from baseline import ref_shims
+    return 'reference' if ref_shims.available() else 'port'
+
+
+def _host_arrays(sizes, rank):
+    rng = np.random.default_rng(7)                       # parameters identical on all ranks
     params = [(rng.standard_normal(k) * 0.05).astype(np.float32) for k in sizes]
-    grads0 = [(rng.standard_normal(k) * 1e-2).astype(np.float32) for k in sizes]
-    opt = naive.MomentumSGD(params, 0.01, 0.9) if optimizer_name == 'momentum_sgd' \
-        else naive.Adam(params)
-    n = sum(sizes)
+    grng = np.random.default_rng(1000 + rank)            # gradients differ per rank
+    grads0 = [(grng.standard_normal(k) * 1e-2).astype(np.float32) for k in sizes]
+    return params, grads0
+
+
+class _RefJob(object):
+    """One rank of the reference's CPU job through the reference's own public API:
+    chainermn.create_communicator('naive') + create_multi_node_optimizer(chainer.optimizers.*)
+    on a chainer.Link holding the workload's parameters
+    (chainermn/optimizers.py:17-33 -> naive_communicator.py:10-17 ->
+    mpi_communicator_base.py:735-778 -> chainer/optimizer.py:857-894 -> update_core_cpu)."""
+
+    def __init__(self, plist, sizes, optimizer_name, rank, world_comm):
+        from baseline import ref_shims
+        chainer, chainermn = ref_shims.import_reference(world_comm)
+        params, self.grads0 = _host_arrays(sizes, rank)
+        link = chainer.Link()
+        with link.init_scope():
+            for i, ((_, shape), a) in enumerate(zip(plist, params)):
+                setattr(link, 'p%05d' % i, chainer.Parameter(a.reshape(shape)))
+        self.params = [p for _, p in sorted(link.namedparams())]
+        comm = chainermn.create_communicator('naive')
+        actual = chainer.optimizers.MomentumSGD(lr=0.01, momentum=0.9) \
+            if optimizer_name == 'momentum_sgd' else chainer.optimizers.Adam()
+        self.opt = chainermn.create_multi_node_optimizer(actual, comm)
+        self.opt.setup(link)
+        self.set_grads()
+        self.opt.update()                                # first call: bcast_data only
+
+    def set_grads(self):
+        for p, g in zip(self.params, self.grads0):
+            p.grad = g.reshape(p.shape).copy()           # fresh gradients every step (untimed)
+
+    def step(self):
+        self.opt.update()
+
+
+class _PortJob(object):
+    """The same job with the NumPy port (oracle/naive.py); used only when baseline/_ref
+    is absent."""
+
+    def __init__(self, plist, sizes, optimizer_name, rank, world, allreduce):
+        from oracle import naive
+        self.naive = naive
+        self.params, self.grads0 = _host_arrays(sizes, rank)
+        self.opt = naive.MomentumSGD(self.params, 0.01, 0.9) if optimizer_name == 'momentum_sgd' \
+            else naive.Adam(self.params)
+        self.world, self.allreduce = world, allreduce
+        self.set_grads()
+
+    def set_grads(self):
+        self.grads = [g.copy() for g in self.grads0]
+
+    def step(self):
+        self.naive.step(self.params, self.grads, self.opt, size=self.world,
+                        allreduce=self.allreduce if self.world > 1 else None)
+
+
+def _time_cpu_job(job, steps, warmup, barrier=None, budget_s=None):
     times = []
     t_start = time.perf_counter()
     i = 0
     while True:
-        grads = [g.copy() for g in grads0]           # fresh gradients every step (untimed)
+        job.set_grads()
+        if barrier is not None:
+            barrier()
         t0 = time.perf_counter()
-        naive.step(params, grads, opt, size=1, allreduce=None)
+        job.step()
+        if barrier is not None:
+            barrier()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -173,51 +291,49 @@ def run_cpu_reference(args, sizes, optimizer_name, budget_s, steps=None, warmup=
                 break
         elif time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
-    ms = 1e3 * float(np.median(times))
-    return n / (ms * 1e-3), ms, len(times)
+    return 1e3 * float(np.median(times)), len(times)
+
+
+def run_cpu_reference(args, plist, sizes, optimizer_name, budget_s=None, steps=None, warmup=1,
+                      kind=None):
+    """The reference's CPU path, one process, one rank.  Returns (ms/step, steps, kind)."""
+    kind = kind or _ref_kind(args)
+    if kind == 'reference':
+        job = _RefJob(plist, sizes, optimizer_name, 0, None)
+    else:
+        job = _PortJob(plist, sizes, optimizer_name, 0, 1, None)
+    ms, done = _time_cpu_job(job, steps, warmup, budget_s=budget_s)
+    return ms, done, kind
 
 
 def reference_worker_main(args):
-    """One CPU rank of the reference arm at N > 1: the `naive` communicator's step
-    (per-parameter in-place Allreduce over the host cores, here gloo in place of MPI,
-    then `*= 1/size` and update_core_cpu).  Launched by reference_main."""
+    """One CPU rank of the reference arm at N > 1 (launched by reference_main)."""
     import torch
     import torch.distributed as dist
-    from oracle import naive
     torch.set_num_threads(1)
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     dist.init_process_group('gloo', rank=rank, world_size=world)
     plist, sizes = workload_sizes(args.workload)
     optimizer_name = args.optimizer or default_optimizer(args.workload)
-    rng = np.random.default_rng(7)
-    params = [(rng.standard_normal(k) * 0.05).astype(np.float32) for k in sizes]
-    grng = np.random.default_rng(1000 + rank)
-    grads0 = [(grng.standard_normal(k) * 1e-2).astype(np.float32) for k in sizes]
-    opt = naive.MomentumSGD(params, 0.01, 0.9) if optimizer_name == 'momentum_sgd' \
-        else naive.Adam(params)
-
-    def allreduce(a):
-        if a.size:
-            dist.all_reduce(torch.from_numpy(a))          # in place, like MPI.IN_PLACE
-
-    times = []
-    for i in range(args.warmup + args.steps):
-        grads = [g.copy() for g in grads0]
-        dist.barrier()
-        t0 = time.perf_counter()
-        naive.step(params, grads, opt, size=world, allreduce=allreduce)
-        dist.barrier()
-        if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
+    kind = _ref_kind(args)
+    if kind == 'reference':
+        from baseline import ref_shims
+        job = _RefJob(plist, sizes, optimizer_name, rank, ref_shims.GlooComm(None))
+    else:
+        def allreduce(a):
+            if a.size:
+                dist.all_reduce(torch.from_numpy(a))      # in place, like MPI.IN_PLACE
+        job = _PortJob(plist, sizes, optimizer_name, rank, world, allreduce)
+    ms, done = _time_cpu_job(job, args.steps, args.warmup, barrier=dist.barrier)
     if rank == 0:
-        print('CPU_REFERENCE_RESULT ' + json.dumps({'ms': 1e3 * float(np.median(times)),
-                                                    'steps': len(times)}), flush=True)
+        print('CPU_REFERENCE_RESULT ' + json.dumps({'ms': ms, 'steps': done, 'kind': kind}),
+              flush=True)
     dist.destroy_process_group()
 
 
 def run_cpu_reference_ranks(args, n_ranks, steps, warmup):
     """N CPU ranks of the reference's naive path on this box's host cores (what
-    `mpiexec -n N` with the `naive` communicator runs); returns (ms/step, steps)."""
+    `mpiexec -n N` with the `naive` communicator runs); returns (ms/step, steps, kind)."""
     import socket
     import subprocess
     s = socket.socket()
@@ -232,7 +348,7 @@ def run_cpu_reference_ranks(args, n_ranks, steps, warmup):
                    CUDA_VISIBLE_DEVICES='')
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference-worker',
                '--gpus', str(n_ranks), '--steps', str(steps), '--warmup', str(warmup),
-               '--workload', args.workload]
+               '--workload', args.workload, '--reference-kind', args.reference_kind]
         if args.optimizer:
             cmd += ['--optimizer', args.optimizer]
         procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE,
@@ -243,7 +359,7 @@ def run_cpu_reference_ranks(args, n_ranks, steps, warmup):
     for line in outs[0].splitlines():
         if line.startswith('CPU_REFERENCE_RESULT '):
             res = json.loads(line[len('CPU_REFERENCE_RESULT '):])
-            return res['ms'], res['steps']
+            return res['ms'], res['steps'], res['kind']
     raise RuntimeError('CPU reference rank 0 printed no result:\n' + outs[0][-2000:])
 
 
@@ -253,44 +369,35 @@ def reference_main(args):
         return
     plist, sizes = workload_sizes(args.workload)
     optimizer_name = args.optimizer or default_optimizer(args.workload)
-    pack_b, upd_b = bytes_per_elem(optimizer_name, 4, True)
+    cfg = make_config(args, optimizer_name, max(1, args.gpus), sizes)
     n = sum(sizes)
     n_ranks = max(1, args.gpus)
+    W, K = max(args.warmup, 0), max(args.steps, 1)
     if n_ranks == 1:
-        steps = max(1, min(args.steps, 50))
-        eps, ms, done = run_cpu_reference(args, sizes, optimizer_name, args.cpu_seconds,
-                                          steps=steps, warmup=max(1, min(args.warmup, 3)))
+        ms, done, kind = run_cpu_reference(args, plist, sizes, optimizer_name, steps=K, warmup=W)
     else:
-        # the reference's CPU job of the same shape: N ranks of the naive communicator
-        ms, done = run_cpu_reference_ranks(args, n_ranks, steps=max(1, min(args.steps, 20)),
-                                           warmup=max(1, min(args.warmup, 2)))
-        eps = n_ranks * n / (ms * 1e-3)
-    gbs = eps * (pack_b + upd_b) / 1e9
-    sample = '{} steps of the full {} workload ({} tensors, {} elements), {} rank{}'.format(
+        ms, done, kind = run_cpu_reference_ranks(args, n_ranks, steps=K, warmup=W)
+    gbs = n_ranks * n * cfg['bytes_per_elem'] / (ms * 1e-3) / 1e9
+    what = ('unmodified chainermn naive communicator + chainer update_core_cpu from baseline/_ref '
+            '(create_multi_node_optimizer(...).update())') if kind == 'reference' else \
+        'NumPy port (oracle/naive.py) of the naive communicator + update_core_cpu'
+    sample = '{} steps of the full {} workload ({} tensors, {} elements), {} rank{}; {}'.format(
         done, args.workload, len(sizes), n, n_ranks,
-        '' if n_ranks == 1 else 's (one process each, gloo allreduce per parameter)')
+        '' if n_ranks == 1 else 's (one process and one host core each, gloo in place of MPI)', what)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': gbs, 'unit': 'GB/s', 'n_gpus': args.gpus,
-        'steps': done, 'warmup': max(1, min(args.warmup, 3)), 'ms_per_step': ms,
+        'steps': done, 'warmup': W, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        'config': {'workload': workload_name(args, optimizer_name, n_ranks), 'n_tensors': len(sizes),
-                   'n_elems': n, 'bytes_per_elem': pack_b + upd_b},
-        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': n_ranks, 'kind': 'port',
+        'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': gbs, 'unit': 'GB/s', 'cores': n_ranks, 'kind': kind,
                          'sample': sample, 'host_cores': os.cpu_count()},
         'e2e': {'value': gbs, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'note': 'NumPy port (oracle/naive.py) of the reference naive communicator + '
-                'update_core_cpu; the reference NumPy path is single-threaded per process, so '
-                'the job uses one host core per rank (N ranks at --gpus N, gloo standing in '
-                'for MPI)',
+        'gpu_launches': 0,
+        'note': 'the reference NumPy path is single-threaded per process: the job uses one host '
+                'core per rank (N ranks at --gpus N); per-parameter in-place Allreduce, *= 1/size, '
+                'update_core_cpu',
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_name(args, optimizer_name, n_gpus):
-    return '{} {} grads, {}, {} (BASELINE configs[{}]) x {} GPU'.format(
-        args.workload, args.allreduce_dtype, optimizer_name, 'pure_nccl',
-        {'resnet50': 1, 'seq2seq': 3, 'mnist_mlp': 0}[args.workload], n_gpus)
 
 
 # ------------------------------------------------------------------ B200 arm --
@@ -305,13 +412,14 @@ def b200_main(args):
             raise SystemExit('--gpus {} needs a torchrun launch with {} ranks'.format(
                 args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
+    # a dead peer must fail the run, not hang the box (in-kernel waits: gp_p2p.cuh)
+    os.environ.setdefault('CHAINER_B200_PEER_TIMEOUT_S', '120')
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group(backend='gloo', rank=rank, world_size=world)
 
     import chainer_b200
     from chainer_b200 import _lib
-    from chainer_b200 import device as dev
     from chainer_b200.core.link import link_from_named_arrays
     lib = _lib.get()
 
@@ -321,6 +429,7 @@ def b200_main(args):
     plist, sizes = workload_sizes(args.workload)
     n = sum(sizes)
     optimizer_name = args.optimizer or default_optimizer(args.workload)
+    cfg = make_config(args, optimizer_name, world, sizes)
     write_grad = not args.no_write_grad
     adt = {'float32': np.float32, 'float16': np.float16, 'bfloat16': 'bfloat16'}[args.allreduce_dtype]
     bsz = 4 if args.allreduce_dtype == 'float32' else 2
@@ -330,6 +439,8 @@ def b200_main(args):
     comm.write_grad = write_grad
     if args.no_p2p:
         comm.use_p2p = False
+    if args.no_step:
+        comm.use_step = False
     if args.multicast != 'auto':
         comm.use_multicast = args.multicast == 'on'
     if args.mc_chunk_mb is not None:
@@ -340,6 +451,9 @@ def b200_main(args):
         lib.gp_p2p_set_tuning(args.p2p_ctas, 512, 1)
     if args.bucket_mb is not None:
         comm.bucket_bytes = int(args.bucket_mb * (1 << 20))
+    for kv in [x for x in args.step_tuning.split(',') if x]:
+        k, v = kv.split('=')
+        lib.gp_step_set_tuning(k.encode(), int(v))
 
     # Arenas in layout order; every parameter / gradient is a view (any device
     # array works -- an arena makes the e2e host copies single transfers).
@@ -410,9 +524,15 @@ def b200_main(args):
         ms_step = float(t.item())
     clocks = sampler.summary(t0, t1)
 
-    # ---- per-kernel timing of the dominant kernel (fused update) ----------------
-    kern = time_kernels(torch, lib, comm, model, actual, opt, set_grads, optimizer_name, n,
-                        bsz, write_grad, reps=min(max(K // 4, 10), 50))
+    # ---- per-kernel timing (CUDA events around each library launch) --------------
+    kern = time_kernels(torch, dist, world, lib, opt, set_grads, reps=min(max(K // 4, 10), 50))
+
+    # ---- parity: J more steps, replayed by the oracle ----------------------------
+    parity = None
+    if not args.no_parity:
+        parity = check_parity(torch, dist, rank, world, comm, opt, actual, optimizer_name, adt,
+                              plist, sizes, offs, p_arena, g_arenas, set_grads, n_sets,
+                              write_grad, steps=args.parity_steps)
 
     # ---- allreduce bus bandwidth (N > 1) ---------------------------------------
     bus = None
@@ -429,6 +549,19 @@ def b200_main(args):
             e2e = {'value': None, 'unit': 'GB/s', 'h2d_bytes_per_step': n * 4,
                    'd2h_bytes_per_step': n * 4, 'error': '%s: %s' % (type(e).__name__, e)}
 
+    # ---- MNBN statistics (BASELINE configs[2]) ----------------------------------
+    mnbn = None
+    if args.mnbn:
+        mnbn = time_mnbn(torch, dist, world, comm, lib)
+
+    # ---- the img/s half of the metric -------------------------------------------
+    train = None
+    if not args.no_train and args.workload == 'resnet50':
+        try:
+            train = time_train(torch, dist, rank, world, comm, args)
+        except Exception as e:      # noqa: BLE001
+            train = {'error': '%s: %s' % (type(e).__name__, e)}
+
     sampler.stop_flag = True
     if rank != 0:
         comm.finalize()
@@ -443,118 +576,290 @@ def b200_main(args):
     peak = peaks.get('hbm_gbs', 6650.0)
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks \
         else 'B200_PROFILING.md fallback 6.65 TB/s (of fallback)'
-    achieved = n * upd_b / (kern['update_us'] * 1e-6) / 1e9
-    traffic = None
+    # the dominant kernel: the launch that takes the most device time per step
+    dom = max(kern['kernels'], key=lambda k: kern['kernels'][k]['us'])
+    dom_us = kern['kernels'][dom]['us']
+    kbytes = {'gp_pack': n * pack_b, 'gp_unpack_momentum_sgd': n * upd_b, 'gp_unpack_adam': n * upd_b,
+              'gp_step_momentum_sgd': n * (pack_b + upd_b), 'gp_step_adam': n * (pack_b + upd_b)}
+    achieved = kbytes[dom] / (dom_us * 1e-6) / 1e9
+    traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        if args.workload == 'resnet50':       # the ncu capture is of the ResNet-50 list
-            traffic = prof.get('{}_{}_{}'.format(optimizer_name, args.allreduce_dtype,
-                                                  'wg' if write_grad else 'nowg'))
+        if args.workload == 'resnet50' and world == 1:   # the ncu captures are of the ResNet-50 list
+            key = '{}:{}_{}_{}'.format(dom, optimizer_name, args.allreduce_dtype,
+                                       'wg' if write_grad else 'nowg')
+            traffic = prof.get(key)
+            if traffic is not None:
+                traffic_src = 'profiles/ncu_traffic.json (ncu --set full capture of this kernel, ' \
+                              'dram__bytes_read.sum + dram__bytes_write.sum; not measured in this run)'
     except Exception:
         pass
+    step_bytes = n * (pack_b + upd_b)
+    roofline = {
+        'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak,
+        'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+        'peak_source': peak_src, 'bytes_per_launch': kbytes[dom], 'us_per_launch': dom_us,
+        'frac_of_nominal_8TBs': achieved / NOMINAL_HBM_GBS,
+        'kernels': {k: dict(v, gbs=kbytes[k] / v['us'] / 1e3, frac=kbytes[k] / v['us'] / 1e3 / peak)
+                    for k, v in kern['kernels'].items()},
+        # the whole step (all launches, gaps included), per GPU
+        'step_gbs_per_gpu': step_bytes / ms_step / 1e6,
+        'step_frac_of_measured': step_bytes / ms_step / 1e6 / peak,
+        'step_frac_of_nominal_8TBs': step_bytes / ms_step / 1e6 / NOMINAL_HBM_GBS,
+    }
+    if dom.startswith('gp_step'):
+        roofline['note'] = (
+            'one launch = the whole step; algorithmic bytes follow SURVEY 8(d) (pack {} + update {} '
+            'B/elem), of which the {} B/elem re-read of the packed buffer is served from L2 (the tile '
+            'was written microseconds earlier by the same kernel), so `achieved` can exceed the DRAM '
+            'peak; expected DRAM traffic {} B/elem'.format(pack_b, upd_b, bsz, pack_b + upd_b - bsz))
+        if world > 1:
+            roofline['note'] += '; at N > 1 the launch also contains the NVLink-bound reduction ' \
+                                '(see `allreduce`), which bounds its duration'
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'GB/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32' if bsz == 4 else args.allreduce_dtype,
-        'data': 'synthetic',
-        'config': {
-            'workload': workload_name(args, optimizer_name, world),
-            'n_tensors': len(sizes), 'n_elems': n, 'packed_bytes': n * bsz,
-            'bytes_per_elem': pack_b + upd_b, 'write_grad': write_grad,
-            'l2': 'working set {} MB per step > 126 MB L2; gradient arrays rotate between {} '
-                  'sets'.format((n * (4 + bsz + 4 + 4 + (4 if optimizer_name == "adam" else 0))) >> 20,
-                                n_sets),
+        'data': 'synthetic', 'config': cfg,
+        'impl_detail': {
             'api': 'create_multi_node_optimizer(MomentumSGD|Adam, pure_nccl).update()',
-            'bucket_bytes': comm.bucket_bytes if world > 1 else None,
-            'allreduce_impl': (None if world == 1 else _allreduce_impl(comm)),
-            'zero_embedding_rows': args.zero_embedding_rows or None,
+            'launches_per_step': kern['launches_per_step'],
+            'one_launch_step': bool(kern['launches_per_step'] == 1),
+            'transport': (None if world == 1 else _allreduce_impl(comm)),
         },
-        'roofline': {
-            'bound': 'hbm', 'kernel': kern['update_kernel'], 'achieved': achieved, 'peak': peak,
-            'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-            'bytes_per_launch': n * upd_b, 'us_per_launch': kern['update_us'],
-            'pack_us': kern['pack_us'], 'pack_gbs': n * pack_b / kern['pack_us'] / 1e3,
-            'pack_frac': n * pack_b / kern['pack_us'] / 1e3 / peak,
-            'frac_of_nominal_8TBs': achieved / 8000.0,
-        },
+        'roofline': roofline,
+        'parity': parity,
         'e2e': e2e,
         'gpu_launches': launches,
         'clocks': clocks,
-        'img_per_s_gradpath_bound': 32.0 * world / (ms_step * 1e-3),
         'host_us_per_step': 1e6 * (t1 - t0) / K,
         'host_enqueue_us_per_step': 1e6 * (t_enq - t0) / K,
     }
+    if train is not None:
+        line['train'] = train
+        if 'img_per_s' in train:
+            line['img_per_s'] = train['img_per_s']
+    if mnbn is not None:
+        line['mnbn'] = mnbn
     if bus is not None:
+        # the step moves S(N+1)/N (multicast) or 2S(N-1)/N (peer memory) bytes per NVLink
+        # direction; implied wire rate if the whole step were the exchange
         line['allreduce'] = bus
-    if not args.no_cpu_baseline:
-        eps, cms, done = run_cpu_reference(args, sizes, optimizer_name, args.cpu_seconds)
+    if not args.no_cpu_baseline and world == 1:
+        cms, done, kind = run_cpu_reference(args, plist, sizes, optimizer_name,
+                                            budget_s=args.cpu_seconds)
         line['cpu_baseline'] = {
-            'value': eps * (pack_b + upd_b) / 1e9, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
-            'ms_per_step': cms, 'host_cores': os.cpu_count(),
-            'sample': '{} steps of the full {} workload on 1 host core (NumPy port of the '
-                      'reference naive communicator + update_core_cpu)'.format(done, args.workload)}
+            'value': n * (pack_b + upd_b) / (cms * 1e-3) / 1e9, 'unit': 'GB/s', 'cores': 1,
+            'kind': kind, 'ms_per_step': cms, 'host_cores': os.cpu_count(),
+            'sample': '{} steps of the full {} workload on 1 host core ({})'.format(
+                done, args.workload,
+                'unmodified chainermn naive communicator + chainer update_core_cpu, baseline/_ref'
+                if kind == 'reference' else 'NumPy port of the naive communicator + update_core_cpu')}
     print(json.dumps(line), flush=True)
     comm.finalize()
 
 
-def time_kernels(torch, lib, comm, model, actual, opt, set_grads, optimizer_name, n, bsz,
-                 write_grad, reps):
-    """Average duration of the pack and the fused-update kernels, CUDA events on
-    the launching (null) stream, measured live by wrapping the library calls."""
-    from chainer_b200 import device as dev
-    rec = {'gp_pack': [], 'upd': []}
-    upd_name = 'gp_unpack_momentum_sgd' if optimizer_name == 'momentum_sgd' else 'gp_unpack_adam'
-    orig_pack, orig_upd = lib.gp_pack, getattr(lib, upd_name)
+STEP_FUNCS = ('gp_step_momentum_sgd', 'gp_step_adam')
+TIMED_FUNCS = ('gp_pack', 'gp_unpack_momentum_sgd', 'gp_unpack_adam') + STEP_FUNCS
 
-    def wrap(fn, key):
+
+def time_kernels(torch, dist, world, lib, opt, set_grads, reps):
+    """Average duration of each library launch of a step, CUDA events on the launching
+    (null) stream, measured live by wrapping the library calls."""
+    from chainer_b200 import device as dev
+    rec = {}
+    orig = {name: getattr(lib, name) for name in TIMED_FUNCS}
+
+    def wrap(name, fn):
         def call(*a):
             stream = a[-1] or 0
             e0, e1 = dev.Event(timing=True), dev.Event(timing=True)
             e0.record(stream)
             r = fn(*a)
             e1.record(stream)
-            rec[key].append((e0, e1))
+            rec.setdefault(name, []).append((e0, e1))
             return r
         return call
-    lib.gp_pack = wrap(orig_pack, 'gp_pack')
-    setattr(lib, upd_name, wrap(orig_upd, 'upd'))
+    for name, fn in orig.items():
+        setattr(lib, name, wrap(name, fn))
     try:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         for k in range(reps):
             set_grads(k)
             opt.update()
         torch.cuda.synchronize()
     finally:
-        lib.gp_pack = orig_pack
-        setattr(lib, upd_name, orig_upd)
-    per_step = max(len(rec['upd']) // reps, 1)
-
-    def total_us(pairs):
-        return sum(a.elapsed_ms(b) for a, b in pairs) * 1e3 / reps
-    return {'pack_us': total_us(rec['gp_pack']), 'update_us': total_us(rec['upd']),
-            'update_kernel': upd_name + (' x%d buckets' % per_step if per_step > 1 else ''),
-            'launches_per_step': per_step}
+        for name, fn in orig.items():
+            setattr(lib, name, fn)
+    out = {}
+    total = 0
+    for name, pairs in rec.items():
+        us = sum(a.elapsed_ms(b) for a, b in pairs) * 1e3 / reps
+        out[name] = {'us': us, 'launches_per_step': len(pairs) // reps}
+        total += len(pairs) // reps
+    return {'kernels': out, 'launches_per_step': total}
 
 
 def _allreduce_impl(comm):
     if comm._p2p is None:
         return 'nccl'
     if comm._mc_active(comm.gpu_buffer_a):
-        return 'nvswitch multicast kernel (gp_mc)'
-    return 'peer-memory kernel (gp_p2p)'
+        return 'nvswitch multicast (multimem.ld_reduce / multimem.st)'
+    return 'nvlink peer memory (rank-order sums)'
+
+
+def _sample_tensors(sizes, budget=1200000):
+    """Indices of the tensors the parity replay follows: the first small ones, the last
+    one of the layout, and mid-size ones up to `budget` elements in total (whole tensors;
+    several tiles and tile boundaries of the step kernels are covered)."""
+    idx = [i for i in range(min(len(sizes), 24)) if sizes[i] <= 4096][:8]
+    idx.append(len(sizes) - 1)
+    total = sum(sizes[i] for i in set(idx))
+    for i in sorted(range(len(sizes)), key=lambda i: -sizes[i]):
+        if i not in idx and 30000 <= sizes[i] <= 600000 and total + sizes[i] <= budget:
+            idx.append(i)
+            total += sizes[i]
+    return sorted(set(i for i in idx if sizes[i] > 0))
+
+
+def check_parity(torch, dist, rank, world, comm, opt, actual, optimizer_name, adt, plist, sizes,
+                 offs, p_arena, g_arenas, set_grads, n_sets, write_grad, steps):
+    """Run `steps` more steps through the SAME public call the timed region used and replay
+    them with the NumPy oracle (oracle/gradpath.py) for a sample of tensors, from the
+    device state before those steps and every rank's gradients of each step.  Bit-exact
+    where the summation order is the oracle's (1 or 2 ranks, peer-memory transport),
+    within the rounding bound of a re-ordered float sum otherwise (NVSwitch / NCCL add in
+    their own order).  Also checks that all ranks hold bit-identical parameters."""
+    from oracle import gradpath as og
+    odt = og.BF16 if adt == 'bfloat16' else np.dtype(adt)
+    idx = _sample_tensors(sizes)
+    sl = [slice(int(offs[i]), int(offs[i + 1])) for i in idx]
+    rules = [p.update_rule for _, p in sorted(opt.target.namedparams())]
+
+    def host(t):
+        return t.detach().cpu().numpy().copy()
+
+    def state_arrays(i, name):
+        st = rules[i].state
+        a = st[name]
+        return a if isinstance(a, torch.Tensor) else torch.as_tensor(a, device='cuda')
+    names = ('v',) if optimizer_name == 'momentum_sgd' else ('m', 'v')
+    torch.cuda.synchronize()
+    hp = [host(p_arena[s]) for s in sl]
+    hs = [{nm: host(state_arrays(i, nm)).reshape(-1) for nm in names} for i in idx]
+    t_now = int(actual.t)
+    exact_order = world <= 2 or (comm._p2p is not None and not comm._mc_active(comm.gpu_buffer_a))
+    exact = exact_order and adt is np.float32
+    max_gerr = 0.0
+    max_perr = 0.0
+    ok = True
+    detail = []
+    perr_acc = [dict() for _ in idx]
+    for j in range(steps):
+        k = 1000 + j
+        mine = [host(g_arenas[k % n_sets][s]) for s in sl]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+        else:
+            gathered = [mine]
+        set_grads(k)
+        opt.update()
+        torch.cuda.synchronize()
+        t_now += 1
+        got_p = [host(p_arena[s]) for s in sl]
+        got_g = [host(g_arenas[k % n_sets][s]) for s in sl] if write_grad else None
+        mean = og.multi_node_mean_grad(gathered, odt)
+        for q, (i, s) in enumerate(zip(idx, sl)):
+            g = mean[q]
+            if optimizer_name == 'momentum_sgd':
+                og.momentum_sgd_update(hp[q], g, hs[q]['v'], 0.01, 0.9)
+            else:
+                og.adam_update_gpu(hp[q], g, hs[q]['m'], hs[q]['v'], t_now)
+            if exact:
+                same = np.array_equal(got_p[q].view(np.uint32), hp[q].view(np.uint32))
+                if write_grad:
+                    same = same and np.array_equal(got_g[q].view(np.uint32), g.view(np.uint32))
+                if not same:
+                    ok = False
+                    detail.append('step %d tensor %s: bits differ' % (j, plist[i][0]))
+                max_perr = max(max_perr, float(np.abs(got_p[q] - hp[q]).max()))
+                continue
+            # re-ordered sum: |mean - oracle mean| <= N * eps * sum_r |g_r| / N (+ the rounding of a
+            # 16-bit buffer), accumulated into the parameters as MomentumSGD / Adam propagate it
+            gmag = np.sum([np.abs(gathered[r][q]) for r in range(world)], axis=0) / world
+            eps = 1.2e-7 if adt is np.float32 else (8e-3 if adt == 'bfloat16' else 1e-3)
+            gerr = world * eps * gmag + (1e-12 if adt is np.float32 else world * 6e-8)
+            if write_grad:
+                d = np.abs(got_g[q] - g)
+                max_gerr = max(max_gerr, float(d.max()))
+                if (d > gerr).any():
+                    ok = False
+                    detail.append('step %d tensor %s: mean gradient off by %.3g' % (
+                        j, plist[i][0], float(d.max())))
+            acc = perr_acc[q]
+            if optimizer_name == 'momentum_sgd':
+                acc['v'] = 0.9 * acc.get('v', 0.0) + 0.01 * gerr
+                acc['p'] = acc.get('p', 0.0) + acc['v']
+                bound = 1.5 * acc['p'] + 4e-7 * np.abs(hp[q]) + 1e-9
+            else:
+                # Adam divides by sqrt(v) + eps: elements with |g| ~ eps amplify the difference
+                bound = 2e-4 + 1e-6 * np.abs(hp[q])
+            d = np.abs(got_p[q] - hp[q])
+            max_perr = max(max_perr, float(d.max()))
+            if (d > bound).any():
+                ok = False
+                detail.append('step %d tensor %s: parameter off by %.3g' % (j, plist[i][0],
+                                                                           float(d.max())))
+            # follow the device values so that the bound stays a per-step bound
+            hp[q] = got_p[q].copy()
+            for nm in names:
+                hs[q][nm] = host(state_arrays(i, nm)).reshape(-1)
+            perr_acc[q] = {}
+    # replicas: every rank holds the same parameter bits
+    replicas = True
+    if world > 1:
+        v = p_arena.view(torch.int32)
+        sig = [int(v.sum(dtype=torch.int64).item()),
+               int((v[::7].to(torch.int64) * 2654435761 % 1000003).sum().item())]
+        sigs = [None] * world
+        dist.all_gather_object(sigs, sig)
+        replicas = all(s == sigs[0] for s in sigs)
+    all_ok = [None] * world
+    if world > 1:
+        dist.all_gather_object(all_ok, bool(ok))
+    else:
+        all_ok = [ok]
+    return {
+        'ok': bool(all(all_ok) and replicas), 'checker': 'oracle/gradpath.py (NumPy restatement of the '
+        'reference, pinned to reference outputs in tests/golden)', 'steps': steps,
+        'tensors': len(idx), 'elements': int(sum(sizes[i] for i in idx)),
+        'mode': 'bit-exact' if exact else 'rounding bound of a re-ordered sum (N*eps*sum|g_r|/N per '
+                                          'step, propagated through the update)',
+        'max_abs_err_param': max_perr, 'max_abs_err_mean_grad': max_gerr,
+        'replicas_identical': bool(replicas), 'ranks_ok': all_ok, 'detail': detail[:4],
+    }
 
 
 def time_allreduce(torch, dist, comm, n, bsz, world):
-    """NCCL-tests convention: algBW = S / t, busBW = algBW * 2(N-1)/N."""
+    """The stand-alone reduction kernel of the transport in use.  NCCL-tests convention:
+    algBW = S / t, busBW = algBW * 2(N-1)/N; `wire_gbs` = bytes that actually cross one
+    NVLink direction of one GPU / t (S(N+1)/N for the in-switch reduction, 2S(N-1)/N for
+    peer memory and rings)."""
     from chainer_b200 import nccl
-    from chainer_b200.communicators import _communication_utility as cu
     buf = comm.gpu_buffer_a
     type_id = 7 if bsz == 4 else 6
     dt = np.float32 if bsz == 4 else np.float16
-    if comm._p2p is not None and comm._mc_active(buf):
+    mc = comm._p2p is not None and comm._mc_active(buf)
+    if mc:
         def one():
             comm._p2p.mc_allreduce(dt, 0, n, None)
     elif comm._p2p is not None:
+        comm._p2p.ensure(buf)
+
         def one():
             comm._p2p.allreduce(dt, 0, n, None)
     else:
@@ -578,9 +883,10 @@ def time_allreduce(torch, dist, comm, n, bsz, world):
     S = n * bsz
     alg = S / us / 1e3
     busbw = alg * 2 * (world - 1) / world
-    return {'impl': _allreduce_impl(comm),
-            'bytes': S, 'us': us, 'alg_gbs': alg, 'bus_gbs': busbw,
-            'frac_of_900': busbw / 900.0, 'frac_of_measured_725': busbw / 725.0}
+    wire = S * ((world + 1.0) / world if mc else 2.0 * (world - 1) / world)
+    return {'impl': _allreduce_impl(comm), 'bytes': S, 'us': us, 'alg_gbs': alg, 'bus_gbs': busbw,
+            'bus_frac_of_900': busbw / NVLINK_GBS, 'wire_bytes_per_direction': wire,
+            'wire_gbs': wire / us / 1e3, 'wire_frac_of_900': wire / us / 1e3 / NVLINK_GBS}
 
 
 def time_e2e(torch, dist, world, opt, params_sorted, p_arena, g_arenas, set_grads, n,
@@ -651,6 +957,143 @@ def time_e2e(torch, dist, world, opt, params_sorted, p_arena, g_arenas, set_grad
             'steps': steps,
             'note': 'H2D(k+1) and D2H(k-1) overlap step k on separate streams; CUDA events, the '
                     'end event waits for the last D2H copies'}
+
+
+def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=5):
+    """The "ResNet-50 img/s" half of the BASELINE metric (configs[1]): a torchvision
+    resnet50 stand-in (random init, synthetic 224x224 batch 32 per GPU) runs forward and
+    backward -- the part the north_star leaves on the framework's own path -- and hands its
+    `.grad` arrays BY POINTER to create_multi_node_optimizer(MomentumSGD, pure_nccl).update()
+    (train_imagenet.py:151-200).  img/s = 32 * N / step time; three device-timed numbers:
+    forward+backward alone, the synchronous step (fwd/bwd then the gradient path), and the
+    reference's double-buffering mode (the exchange of step k overlaps fwd/bwd of step k+1,
+    chainermn/optimizers.py:59-146)."""
+    import torchvision
+    import chainer_b200
+    from chainer_b200.core.link import link_from_named_arrays
+    torch.manual_seed(7)
+    net = torchvision.models.resnet50(weights=None).cuda().to(memory_format=torch.channels_last)
+    net.train()
+    x = torch.randn(batch, 3, 224, 224, device='cuda').to(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (batch,), device='cuda')
+    named = [(nm.replace('.', '/'), p) for nm, p in net.named_parameters()]
+    n_params = sum(p.numel() for _, p in named)
+
+    def fwd_bwd():
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss.backward()
+        return loss
+
+    out = {'model': 'torchvision resnet50 stand-in ({} tensors, {} parameters), batch {}/GPU, '
+                    'synthetic 224x224, bf16 autocast forward/backward (channels_last), fp32 '
+                    'parameters, gradients and MomentumSGD state'.format(len(named), n_params, batch),
+           'batch_per_gpu': batch, 'steps': steps}
+
+    def run(mode):
+        model = link_from_named_arrays([('/' + nm, p.data) for nm, p in named])
+        plink = [p for _, p in sorted(model.namedparams())]
+        tparam = [p for _, p in sorted((('/' + nm), p) for nm, p in named)]
+        actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9)
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm,
+                                                       double_buffering=(mode == 'double_buffering'))
+        opt.setup(model)
+
+        def one(update=True):
+            for tp in tparam:
+                tp.grad = None                            # cleargrads(): new gradient arrays
+            loss = fwd_bwd()
+            if update:
+                for lp, tp in zip(plink, tparam):
+                    lp.grad = tp.grad
+                opt.update()
+            return loss
+        for _ in range(warmup):
+            one(mode != 'fwd_bwd')
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one(mode != 'fwd_bwd')
+        e1.record()
+        torch.cuda.synchronize()
+        if hasattr(opt, 'wait'):
+            opt.wait()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        assert bool(torch.isfinite(loss).item())
+        return ms
+    fb = run('fwd_bwd')
+    sync = run('sync')
+    out.update({'fwd_bwd_ms': fb, 'step_ms': sync, 'gradpath_ms': sync - fb,
+                'gradpath_share': (sync - fb) / sync, 'img_per_s': batch * world / (sync * 1e-3),
+                'img_per_s_fwd_bwd_only': batch * world / (fb * 1e-3)})
+    try:
+        db = run('double_buffering')
+        out.update({'step_ms_double_buffering': db,
+                    'img_per_s_double_buffering': batch * world / (db * 1e-3)})
+    except Exception as e:      # noqa: BLE001
+        out['double_buffering_error'] = '%s: %s' % (type(e).__name__, e)
+    return out
+
+
+def time_mnbn(torch, dist, world, comm, lib, batch=32):
+    """BASELINE configs[2]: the MultiNodeBatchNormalization statistics of one ResNet-50
+    step -- 53 layers, forward [mean | E x^2] and backward [sum gy | sum gy x_hat], each
+    followed by the exchange of its 2C floats over the N ranks -- through the functions the
+    link calls (chainer_b200/functions/batch_normalization.py)."""
+    from chainer_b200 import workloads
+    from chainer_b200.functions.batch_normalization import _NcclImpl
+    impl = _NcclImpl(comm)
+    layers = workloads.resnet50_bn_layers(batch)
+    uniq = {}
+    for _, s in layers:
+        if s not in uniq:
+            x = torch.randn(*s, device='cuda')
+            gy = torch.randn(*s, device='cuda') * 1e-3
+            gamma = torch.ones(s[1], device='cuda')
+            mean, var = impl.get_mean_and_var(None, gamma, x)
+            uniq[s] = (x, gy, gamma, mean, torch.rsqrt(var + 2e-5))
+
+    def one_step():
+        for _, s in layers:
+            x, gy, gamma, mean, inv_std = uniq[s]
+            impl.get_mean_and_var(None, gamma, x)
+        for _, s in reversed(layers):
+            x, gy, gamma, mean, inv_std = uniq[s]
+            impl.get_ggamma_and_gbeta_from_x(None, gamma, gy, x, mean, inv_std)
+    for _ in range(3):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 10
+    c0 = lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        one_step()
+    e1.record()
+    t_enq = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    if world > 1:
+        t = torch.tensor([us], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+    nbytes = sum(int(np.prod(s)) * 4 for _, s in layers)
+    return {'layers': len(layers), 'us_per_step': us, 'launches_per_step': (lib.launches - c0) // reps,
+            'host_enqueue_us_per_step': 1e6 * t_enq / reps,
+            'activation_bytes_read': 3 * nbytes,
+            'note': 'statistics of 53 BN layers forward + backward at batch %d incl. the exchange of '
+                    '2C floats per layer and direction over %d rank(s); device time, host-enqueue '
+                    'bound when us_per_step ~ host_enqueue_us_per_step' % (batch, world)}
 
 
 def main():

@@ -141,6 +141,16 @@ PROTOTYPES = {
     'gp_mc_destroy': (c_int, [c_void_p]),
     'gp_mc_allreduce': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     'gp_mc_set_tuning': (c_int, [c_int, c_int, c_int]),
+    'gp_step_supported': (c_int, [c_int, c_int, c_int, c_double, c_int]),
+    'gp_step_momentum_sgd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                     c_int64, c_double, c_double, c_double, c_int, c_int, c_void_p]),
+    'gp_step_adam': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
+                             c_double, c_double, c_double, c_double, c_double, c_double, c_double,
+                             c_double, c_double, c_int, c_int, c_int, c_void_p]),
+    'gp_step_words_bytes': (c_size_t, [c_int64]),
+    'gp_step_tile_elems': (c_int, []),
+    'gp_p2p_set_step_words': (c_int, [c_void_p, _P(c_void_p), c_int64, c_int64]),
+    'gp_step_set_tuning': (c_int, [c_char_p, c_int]),
     'gp_nccl_comm_window_register': (c_int, [c_void_p, c_void_p, c_size_t, _P(c_void_p), c_int]),
     'gp_nccl_comm_window_deregister': (c_int, [c_void_p, c_void_p]),
     'gp_ipc_get_handle': (c_int, [c_void_p, c_char_p]),
@@ -166,11 +176,11 @@ KERNEL_FUNCS = frozenset([
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
     'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce',
     'gp_unpack_momentum_sgd_hooked', 'gp_unpack_adam_hooked', 'gp_sqnorm', 'gp_scale_by_device',
-    'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family'])
+    'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family', 'gp_step_momentum_sgd', 'gp_step_adam'])
 
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',
-             'gp_sqnorm_workspace_bytes'}
+             'gp_sqnorm_workspace_bytes', 'gp_step_supported', 'gp_step_words_bytes', 'gp_step_tile_elems'}
 
 
 class GradpathError(RuntimeError):
@@ -248,6 +258,10 @@ def load():
                 '`python -c "import __graft_entry__ as g; g.build()"` or '
                 '`make -C chainer_b200/csrc`.  chainer_b200 has no fallback path.'.format(path))
         _lib = _Lib(path)
+        # wall-time bound of the in-kernel waits for peer GPUs (default 30 minutes; 0: none)
+        t = os.environ.get('CHAINER_B200_PEER_TIMEOUT_S')
+        if t:
+            _lib.gp_set_tuning(b'peer_timeout_s', int(float(t)))
     return _lib
 
 

@@ -248,7 +248,8 @@ class DeviceMemory(object):
     def assign(self, size):
         if size > self.size:
             alloc = self.allocator(size) if self.allocator is not None else None
-            self._alloc = alloc if alloc is not None else _dev._Allocation(size)
+            # capacity in whole 16-byte vectors: the collective kernels round the tail up
+            self._alloc = alloc if alloc is not None else _dev._Allocation((size + 15) // 16 * 16)
             self.memory = _dev._MemPtr(self._alloc.ptr, self._alloc)
             self.size = size
 

@@ -84,6 +84,11 @@ class PeerAllreduce(object):
         self.multicast_error = None
         self._mc = None                 # current _McAllocation
         self._mc_serial = 0
+        # per-tile words of the one-launch step (csrc/gp_step.cu)
+        self._step_alloc = None
+        self._step_maps = []
+        self._step_cap = 0
+        self._step_tile = 0
 
     # -- IPC plumbing -------------------------------------------------------------
     def _exchange(self, ptr):
@@ -250,6 +255,30 @@ class PeerAllreduce(object):
         self.lib.gp_p2p_allreduce(self.handle, _dev.dtype_id(dtype), offset_elems, n_elems,
                                   _dev.stream_ptr(stream))
 
+    # -- one-launch step -----------------------------------------------------------
+    def step_prepare(self, n_elems):
+        """Collective when it (re)allocates: per-tile counters / flags of the one-launch
+        step for a packed buffer of `n_elems` elements.  Every rank takes the same
+        decision (same element count, same tuning)."""
+        lib = self.lib
+        tile = lib.gp_step_tile_elems()
+        need = (n_elems + tile - 1) // tile
+        if self._step_alloc is not None and tile == self._step_tile and need <= self._step_cap:
+            return
+        lib.gp_device_synchronize()
+        self._close(self._step_maps)
+        self._step_maps = []
+        self.mpi_comm.barrier()          # nobody still signals into the old words
+        cap = max(need * 2, 1024)
+        nbytes = lib.gp_step_words_bytes(cap)
+        self._step_alloc = _dev._Allocation(nbytes)
+        lib.gp_memset_async(self._step_alloc.ptr, 0, nbytes, 0)
+        lib.gp_stream_synchronize(0)
+        ptrs, self._step_maps = self._exchange(self._step_alloc.ptr)
+        lib.gp_p2p_set_step_words(self.handle, (ctypes.c_void_p * self.size)(*ptrs), cap, tile)
+        self._step_cap, self._step_tile = cap, tile
+        self.mpi_comm.barrier()          # every rank's words are zeroed and mapped
+
     def allreduce_small(self, in_ptr, out_ptr, n_elems, C, scale, stream):
         """out = scale * sum over ranks of in (float32, n_elems <= small_cap); with
         C > 0 additionally out[C:] -= out[:C]**2 (mean | var)."""
@@ -267,6 +296,8 @@ class PeerAllreduce(object):
         self._close(self._flag_maps)
         self._close(self._small_maps)
         self._close(self._small_flag_maps)
+        self._close(self._step_maps)
+        self._step_maps, self._step_alloc = [], None
         self._buf_maps, self._flag_maps = [], []
         self._small_maps, self._small_flag_maps = [], []
         self.mpi_comm.barrier()

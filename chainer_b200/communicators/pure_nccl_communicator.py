@@ -118,6 +118,10 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
         # multicast path: pipeline chunk (0: one kernel; None: two chunks from 32 MB
         # up -- measured best at N = 4 and 8, profiles/r01_bench_n{4,8}_mc*.json)
         self.mc_chunk_bytes = None
+        # one-launch step (csrc/gp_step.cu): pack -> sum over ranks -> fused update as ONE
+        # kernel per rank, tile by tile.  None: whenever it covers the configuration
+        # (or as CHAINER_B200_STEP says); False: the separate launches
+        self.use_step = None
 
     # ------------------------------------------------------------ lifecycle --
     def finalize(self):
@@ -727,12 +731,59 @@ class _FusedPlan(object):
                 if end == n_elems:
                     for key, t in launches:
                         launch(key, t, 0, t.n_elems)
+        if (not hooked and len(launches) == 1 and not config.is_debug() and
+                self._run_step(lib, launches[0][0], launches[0][1], dtype, buf_id, scale, wg,
+                               n_elems, stream)):
+            return True
         comm._pipeline(pd, dtype, stream, consume)
+        return True
+
+    def _run_step(self, lib, key, t, dtype, buf_id, scale, wg, n_elems, stream):
+        """The whole step as ONE launch (csrc/gp_step.cu) when it covers this
+        configuration: float32 arrays, float32 / float16 / bfloat16 buffer, MomentumSGD or
+        Adam without hooks, 1 rank or 2 / 4 / 8 ranks of one NVSwitch box.  False: not
+        covered, nothing launched.  The decision depends only on replicated state, so all
+        ranks take it together."""
+        comm = self.comm
+        want = comm.use_step
+        if want is None:
+            want = _step_enabled_by_env()
+        if not want or key[0] not in ('momentum_sgd', 'adam'):
+            return False
+        hint = t.layout_hint(dtype)
+        adam_flags = key[9] if key[0] == 'adam' else 0
+        if not lib.gp_step_supported(comm.size, buf_id, hint, scale, adam_flags):
+            return False
+        buf = comm.gpu_buffer_a
+        handle = mc_ptr = None
+        if comm.size > 1:
+            p2p = comm._p2p
+            if p2p is None:
+                return False
+            if comm._mc_active(buf):
+                mc_ptr = buf._alloc.mc_ptr
+            else:
+                p2p.ensure(buf, stream)
+            p2p.step_prepare(n_elems)
+            handle = p2p.handle
+        sp = stream.ptr
+        if key[0] == 'momentum_sgd':
+            lib.gp_step_momentum_sgd(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs,
+                                     t.n_params, n_elems, scale, key[1], key[2], wg, hint, sp)
+        else:
+            lib.gp_step_adam(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs, t.n_params,
+                             n_elems, scale, key[1], key[2], key[3], key[4], key[5], key[6],
+                             key[7], key[8], key[9], wg, hint, sp)
         return True
 
 
 class _PlanStale(Exception):
     pass
+
+
+def _step_enabled_by_env():
+    import os
+    return os.environ.get('CHAINER_B200_STEP', '1') not in ('0', '', 'false', 'False')
 
 
 _NONE_ID = id(None)

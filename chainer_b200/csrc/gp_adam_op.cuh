@@ -5,9 +5,6 @@
 
 namespace {
 
-template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
-  return reinterpret_cast<P*>(p);
-}
 
 // ------------------------------------------------------------------- Adam --
 template <class P> struct AdamT { using type = float; };

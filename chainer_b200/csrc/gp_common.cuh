@@ -15,6 +15,14 @@
 
 #include "../../include/gradpath.h"
 
+// table entries carry pointers as uint64
+template <class P> __device__ __forceinline__ const P* cptr(uint64_t p) {
+  return reinterpret_cast<const P*>(p);
+}
+template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
+  return reinterpret_cast<P*>(p);
+}
+
 // ----------------------------------------------------------------- errors --
 void gp_set_error(const char* fmt, ...);
 int gp_cuda_fail(cudaError_t e, const char* what);
@@ -34,6 +42,8 @@ struct GpTuning {
   int bn_ctas_per_sm;
 };
 extern GpTuning g_gp_tuning;
+// wall-time bound of the in-kernel waits for peer GPUs, ns (0: unbounded); gp_set_tuning("peer_timeout_s")
+extern unsigned long long g_gp_peer_timeout_ns;
 int gp_sm_count_cached();
 
 // ------------------------------------------------------------ dtype traits --

@@ -394,6 +394,7 @@ int gp_mc_allreduce(void* p2p_comm, void* mc, int dtype, int64_t offset_elems, i
   a.p.rank = c->rank;
   a.p.n = c->n;
   a.p.epoch = ++c->epoch;
+  a.p.timeout_ns = g_gp_peer_timeout_ns;
   for (int k = 0; k < c->n; ++k) {
     a.p.bufs[k] = nullptr;
     a.p.flags[k] = c->flags[k];

@@ -174,6 +174,7 @@ struct SmallArgs {
   int rank, n;
   int64_t cap;
   uint32_t epoch;
+  unsigned long long timeout_ns;
   const float* in;
   float* out;
   int n_elems;
@@ -195,11 +196,7 @@ __global__ void __launch_bounds__(1024) p2p_small_kernel(const SmallArgs a) {
   if (threadIdx.x < a.n) {
     __threadfence_system();
     st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
-    const uint32_t* f = a.flags[a.rank] + threadIdx.x;
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
-      if (clock64() - t0 > 20000000000LL) __trap();
-    }
+    spin_until(a.flags[a.rank] + threadIdx.x, a.epoch, a.timeout_ns);
   }
   __syncthreads();
   // 2. rank-order sum of the N slots, scale (x * (1.0/N) in double or exactly in
@@ -286,6 +283,9 @@ int gp_p2p_create(void** comm, int rank, int n_ranks, void* const* buffers, void
   c->epoch = 0;
   c->small_cap = 0;
   c->small_epoch = 0;
+  c->step_tile_cap = 0;
+  c->step_tile_elems = 0;
+  c->step_epoch = 0;
   for (int k = 0; k < n_ranks; ++k) {
     c->bufs[k] = buffers[k];
     c->flags[k] = (uint32_t*)flags[k];
@@ -320,6 +320,7 @@ int gp_p2p_allreduce(void* comm, int dtype, int64_t offset_elems, int64_t n_elem
   a.rank = c->rank;
   a.n = c->n;
   a.epoch = ++c->epoch;
+  a.timeout_ns = g_gp_peer_timeout_ns;
   for (int k = 0; k < c->n; ++k) {
     a.bufs[k] = (char*)c->bufs[k] + offset_elems * isz;
     a.flags[k] = c->flags[k];
@@ -392,6 +393,7 @@ int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elem
   a.n = c->n;
   a.cap = c->small_cap;
   a.epoch = ++c->small_epoch;
+  a.timeout_ns = g_gp_peer_timeout_ns;
   a.in = (const float*)in;
   a.out = (float*)out;
   a.n_elems = (int)n_elems;

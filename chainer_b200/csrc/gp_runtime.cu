@@ -31,6 +31,9 @@ int gp_cuda_fail(cudaError_t e, const char* what) {
 GpTuning g_gp_tuning = {/*threads*/ 256, /*unroll*/ 0, /*ctas_per_sm*/ 16, /*persistent*/ 0,
                         /*bn_threads*/ 256, /*pipeline*/ 0, /*bn_ctas_per_sm*/ 4};
 
+// 30 minutes: a collective watchdog, not a skew limit (gp_p2p.cuh: spin_until)
+unsigned long long g_gp_peer_timeout_ns = 1800ull * 1000000000ull;
+
 gpb::BulkTuning gpb::g_bulk_tuning = {/*enable*/ 0, /*tile*/ 4096, /*stages*/ 4, /*ctas*/ 1, /*debug*/ 0, /*chunk*/ 2048};
 
 int gp_sm_count_cached() {
@@ -62,6 +65,7 @@ int gp_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "bn_threads")) g_gp_tuning.bn_threads = value;
   else if (!strcmp(key, "pipeline")) g_gp_tuning.pipeline = value;
   else if (!strcmp(key, "bn_ctas_per_sm")) g_gp_tuning.bn_ctas_per_sm = value < 1 ? 1 : value;
+  else if (!strcmp(key, "peer_timeout_s")) g_gp_peer_timeout_ns = value <= 0 ? 0ull : (unsigned long long)value * 1000000000ull;
   else if (!strcmp(key, "bulk")) gpb::g_bulk_tuning.enable = value;
   else if (!strcmp(key, "bulk_tile")) gpb::g_bulk_tuning.tile = value < 512 ? 512 : (value & ~511);
   else if (!strcmp(key, "bulk_stages")) gpb::g_bulk_tuning.stages = value < 2 ? 2 : value;
@@ -83,6 +87,7 @@ int gp_get_tuning(const char* key, int* value) {
   else if (!strcmp(key, "bn_threads")) *value = g_gp_tuning.bn_threads;
   else if (!strcmp(key, "pipeline")) *value = g_gp_tuning.pipeline;
   else if (!strcmp(key, "bn_ctas_per_sm")) *value = g_gp_tuning.bn_ctas_per_sm;
+  else if (!strcmp(key, "peer_timeout_s")) *value = (int)(g_gp_peer_timeout_ns / 1000000000ull);
   else if (!strcmp(key, "bulk")) *value = gpb::g_bulk_tuning.enable;
   else if (!strcmp(key, "bulk_tile")) *value = gpb::g_bulk_tuning.tile;
   else if (!strcmp(key, "bulk_stages")) *value = gpb::g_bulk_tuning.stages;

@@ -23,9 +23,6 @@
 
 namespace {
 
-template <class P> __device__ __forceinline__ P* mptr(uint64_t p) {
-  return reinterpret_cast<P*>(p);
-}
 
 template <int KIND>
 struct FamilyOp {

@@ -1,0 +1,513 @@
+// gp_step.cu -- the whole per-step gradient path as ONE launch per rank:
+//   pack (+cast)  ->  sum over ranks  ->  unpack + 1/N + optimizer update
+// flowing tile by tile through the packed buffer instead of kernel by kernel.
+//
+// Reference being replaced (chainer v7.8.1), one step of
+// `_MultiNodeOptimizer.update` (chainermn/optimizers.py:17-33):
+//   pack      chainermn/communicators/_memory_utility.py:253-268, 289-358
+//   allreduce chainermn/communicators/pure_nccl_communicator.py:180-182
+//   1/N       chainermn/communicators/pure_nccl_communicator.py:183-189
+//   unpack    chainermn/communicators/_memory_utility.py:271-286, 361-429
+//   update    chainer/optimizers/momentum_sgd.py:75-88, chainer/optimizers/adam.py:224-332
+// (3 + n_params launches and a kernel boundary between every stage there).
+//
+// The packed buffer is cut into TILES of `tile_elems` elements (a multiple of 4096:
+// 16-byte vectors for every buffer dtype, whole walker tiles).
+//
+// One rank (gp_step*, comm == NULL): a CTA packs tile t and, after a CTA barrier,
+// runs the fused update on the same tile: the packed values are read back from
+// L1/L2, never from HBM, and there is no kernel boundary between the stages.
+//
+// N ranks (2, 4, 8 on one NVSwitch box): tile t is OWNED by rank t % N.
+//   worker CTAs   pack their tiles in tile order; after each tile one
+//                 `red.release.sys.add` on the owner's counter cnt[t];
+//                 then, per tile, wait for the owner's flag[t] and run the fused
+//                 update on it;
+//   reducer CTAs  (the first `reducers` CTAs) take the rank's own tiles in order:
+//                 wait until cnt[t] shows all N ranks have packed it, sum the N
+//                 copies -- `multimem.ld_reduce` + `multimem.st` through the NVSwitch
+//                 (transport MC) or N peer loads added in rank order + N peer stores
+//                 (transport P2P, bit-exact with the oracle) -- then publish
+//                 flag[t] = epoch to every rank.
+// The NVLink-bound reduction of tile t therefore overlaps the HBM-bound pack of later
+// tiles and update of earlier ones inside ONE launch, with no kernel-level barrier
+// (the allreduce kernels need two) and no chunk launches.  Counters and flags are
+// monotonic (cnt[t] == N * epoch, flag[t] == epoch after step `epoch`), live in a
+// per-rank block shared through CUDA IPC, and every wait polls LOCAL memory.
+// Every CTA of the launch is resident at once (the grid is capped by the occupancy),
+// which the cross-rank waits require.
+#include <string.h>
+
+#include "gp_pack_op.cuh"
+#include "gp_sgd_op.cuh"
+#include "gp_adam_op.cuh"
+
+namespace {
+
+#include "gp_p2p.cuh"
+
+constexpr int kStepThreads = 256;
+
+struct StepTables {
+  const int64_t* csum;
+  const gp_seg_t* segs;
+  int n_segs;
+  int use_smem;
+  int64_t n_elems;
+  int64_t tile_elems;
+  int64_t n_tiles;
+};
+
+__device__ __forceinline__ const int64_t* stage_csum(const StepTables& a, int64_t* s_csum) {
+  if (!a.use_smem) return a.csum;
+  for (int i = threadIdx.x; i <= a.n_segs; i += blockDim.x) s_csum[i] = a.csum[i];
+  __syncthreads();
+  return s_csum;
+}
+
+// ------------------------------------------------------------------ one rank --
+template <class Upd, class B, int SM>
+__global__ void __launch_bounds__(kStepThreads) step1_kernel(const StepTables a, const PackOp pk,
+                                                            const Upd up) {
+  extern __shared__ int64_t s_csum[];
+  const int64_t* cs = stage_csum(a, s_csum);
+  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int64_t lo = t * a.tile_elems;
+    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+    gpw::walk_range<PackOp, B, 4, 0, GP_F32>(cs, a.segs, a.n_segs, lo, hi, pk);
+    __syncthreads();   // the CTA's packed values are visible to all its threads
+    gpw::walk_range<Upd, B, Upd::kDefaultUnroll, SM, GP_F32>(cs, a.segs, a.n_segs, lo, hi, up);
+  }
+}
+
+// ------------------------------------------------------------------- N ranks --
+struct StepPeers {
+  uint32_t* words[kMaxRanks];  // every rank's [cnt: tile_cap | flag: tile_cap]
+  void* bufs[kMaxRanks];       // P2P: this process's mappings of the packed buffers
+  char* mc_base;               // MC: multicast address of the packed buffer
+  int64_t tile_cap;
+  int rank, n;
+  uint32_t epoch;
+  int reducers;
+  unsigned long long timeout_ns;
+};
+
+// 16-byte multimem accessors (see gp_mc.cu)
+template <class T> struct Mm;
+template <> struct Mm<float> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Mm<__half> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Mm<__nv_bfloat16> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+__device__ __forceinline__ void mm_st(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Transport MC: the switch adds the N copies and replicates the sum.  Software
+// pipelined: the loads of the next UN vectors are in flight while the current UN
+// are stored, so both NVLink directions stay busy.
+template <class B, int UN>
+struct RedMc {
+  static __device__ __forceinline__ void load(uint4 (&x)[UN], const char* base, int64_t i, int64_t v1) {
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t v = i + (int64_t)u * kStepThreads;
+      if (v < v1) x[u] = Mm<B>::ld_reduce(base + v * 16);
+    }
+  }
+  static __device__ __forceinline__ void store(const uint4 (&x)[UN], char* base, int64_t i, int64_t v1) {
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t v = i + (int64_t)u * kStepThreads;
+      if (v < v1) mm_st(base + v * 16, x[u]);
+    }
+  }
+  static __device__ __forceinline__ void run(const StepPeers& p, int64_t v0, int64_t v1) {
+    constexpr int64_t adv = (int64_t)kStepThreads * UN;
+    int64_t i = v0 + threadIdx.x;
+    if (i >= v1) return;
+    uint4 x[UN], y[UN];
+    load(x, p.mc_base, i, v1);
+    while (true) {
+      load(y, p.mc_base, i + adv, v1);
+      store(x, p.mc_base, i, v1);
+      i += adv;
+      if (i >= v1) break;
+      load(x, p.mc_base, i + adv, v1);
+      store(y, p.mc_base, i, v1);
+      i += adv;
+      if (i >= v1) break;
+    }
+  }
+};
+
+// Transport P2P: N peer loads, added in RANK ORDER (the oracle's order: identical bits
+// on every rank and for every N), N peer stores.
+template <class T> struct Vec16;
+template <> struct Vec16<float> {
+  static __device__ __forceinline__ void add(uint4& acc, const uint4& x) {
+    float4& a = reinterpret_cast<float4&>(acc);
+    const float4& b = reinterpret_cast<const float4&>(x);
+    a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y);
+    a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+  }
+};
+template <> struct Vec16<__half> {
+  static __device__ __forceinline__ void add(uint4& acc, const uint4& x) {
+    __half2* a = reinterpret_cast<__half2*>(&acc);
+    const __half2* b = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hadd2_rn(a[i], b[i]);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static __device__ __forceinline__ void add(uint4& acc, const uint4& x) {
+    __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&acc);
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hadd2_rn(a[i], b[i]);
+  }
+};
+__device__ __forceinline__ uint4 ld_sys(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(uint4* p, const uint4& v) {
+  asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w) : "memory");
+}
+template <class B, int N>
+struct RedP2p {
+  static __device__ __forceinline__ void run(const StepPeers& p, int64_t v0, int64_t v1) {
+    constexpr int UN = N >= 4 ? 2 : 4;
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += (int64_t)kStepThreads * UN) {
+      uint4 x[UN][N];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t v = i + (int64_t)u * kStepThreads;
+        if (v < v1) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) x[u][k] = ld_sys(reinterpret_cast<const uint4*>(p.bufs[k]) + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t v = i + (int64_t)u * kStepThreads;
+        if (v < v1) {
+          uint4 acc = x[u][0];
+#pragma unroll
+          for (int k = 1; k < N; ++k) Vec16<B>::add(acc, x[u][k]);
+#pragma unroll
+          for (int k = 0; k < N; ++k) st_sys(reinterpret_cast<uint4*>(p.bufs[k]) + v, acc);
+        }
+      }
+    }
+  }
+};
+
+template <class Upd, class B, class Red>
+__global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a, const StepPeers p,
+                                                            const PackOp pk, const Upd up) {
+  extern __shared__ int64_t s_csum[];
+  if ((int)blockIdx.x < p.reducers) {
+    // ------------------------------------------------------------- reducer ----
+    const uint32_t* cnt = p.words[p.rank];
+    const uint32_t all_packed = p.epoch * (uint32_t)p.n;
+    constexpr int E = 16 / (int)sizeof(B);
+    for (int64_t t = p.rank + (int64_t)blockIdx.x * p.n; t < a.n_tiles; t += (int64_t)p.reducers * p.n) {
+      if (threadIdx.x == 0) spin_until(cnt + t, all_packed, p.timeout_ns);
+      __syncthreads();
+      const int64_t lo = t * a.tile_elems;
+      const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+      // whole 16-byte vectors: the tail of the last tile is rounded up into the padding
+      // of the buffer (never read back)
+      Red::run(p, lo / E, (hi + E - 1) / E);
+      __syncthreads();
+      // release: cumulative over the CTA's stores (ordered before it by bar.sync)
+      if ((int)threadIdx.x < p.n) st_release_sys(p.words[threadIdx.x] + p.tile_cap + t, p.epoch);
+    }
+    return;
+  }
+  // ---------------------------------------------------------------- worker ----
+  const int64_t* cs = stage_csum(a, s_csum);
+  const int64_t w = (int64_t)blockIdx.x - p.reducers;
+  const int64_t nw = (int64_t)gridDim.x - p.reducers;
+  for (int64_t t = w; t < a.n_tiles; t += nw) {
+    const int64_t lo = t * a.tile_elems;
+    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+    gpw::walk_range<PackOp, B, 4, 0, GP_F32>(cs, a.segs, a.n_segs, lo, hi, pk);
+    __syncthreads();
+    if (threadIdx.x == 0) red_add_release_sys(p.words[t % p.n] + t, 1u);
+  }
+  const uint32_t* flag = p.words[p.rank] + p.tile_cap;
+  for (int64_t t = w; t < a.n_tiles; t += nw) {
+    // the acquire also drops this SM's L1 lines of the tile (written by pack earlier)
+    if (threadIdx.x == 0) spin_until(flag + t, p.epoch, p.timeout_ns);
+    __syncthreads();
+    const int64_t lo = t * a.tile_elems;
+    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+    gpw::walk_range<Upd, B, Upd::kDefaultUnroll, 1, GP_F32>(cs, a.segs, a.n_segs, lo, hi, up);
+  }
+}
+
+// ------------------------------------------------------------------ launching --
+struct StepTuning {
+  int tile_elems;   // multiple of 4096
+  int reducers;     // reducer CTAs per rank (N ranks)
+  int unroll;       // MC transport: 16-byte vectors per thread and pipeline stage (4, 8)
+  int ctas_per_sm;  // cap of resident CTAs per SM (0: the occupancy)
+  int tile1_elems;  // one rank: tile size
+  int grid1;        // one rank: 0 = one CTA per tile, else persistent CTAs per SM
+};
+StepTuning g_step = {16384, 32, 4, 4, 8192, 0};
+
+template <class K>
+int occupancy(K kernel, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kStepThreads, smem) != cudaSuccess ||
+      occ < 1) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
+  return occ;
+}
+
+StepTables make_tables(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t n_elems,
+                       int64_t tile, size_t* smem) {
+  StepTables a;
+  a.csum = d_csum;
+  a.segs = d_segs;
+  a.n_segs = n_segs;
+  a.use_smem = n_segs <= gpw::kMaxSmemSegs;
+  a.n_elems = n_elems;
+  a.tile_elems = tile;
+  a.n_tiles = (n_elems + tile - 1) / tile;
+  *smem = a.use_smem ? (size_t)(n_segs + 1) * sizeof(int64_t) : 0;
+  return a;
+}
+
+template <class Upd, class B>
+int launch_step1(const StepTables& a, size_t smem, const PackOp& pk, const Upd& up, cudaStream_t st) {
+  auto launch = [&](auto kernel) {
+    int64_t grid = a.n_tiles;
+    if (g_step.grid1 > 0) {
+      int occ = occupancy(kernel, smem);
+      if (g_step.grid1 < occ) occ = g_step.grid1;
+      const int64_t cap = (int64_t)gp_sm_count_cached() * occ;
+      if (grid > cap) grid = cap;
+    }
+    if (grid > 0x7fffffff) grid = 0x7fffffff;
+    kernel<<<(unsigned)grid, kStepThreads, smem, st>>>(a, pk, up);
+    return gp_cuda_fail(cudaGetLastError(), "step1_kernel launch");
+  };
+  if (up.s.mode == 0) return launch(step1_kernel<Upd, B, 0>);
+  return launch(step1_kernel<Upd, B, 1>);
+}
+
+template <class Upd, class B, class Red>
+int launch_stepn_t(const StepTables& a, StepPeers p, size_t smem, const PackOp& pk, const Upd& up,
+                   cudaStream_t st) {
+  auto kernel = stepn_kernel<Upd, B, Red>;
+  int occ = occupancy(kernel, smem);
+  if (g_step.ctas_per_sm > 0 && g_step.ctas_per_sm < occ) occ = g_step.ctas_per_sm;
+  const int64_t cap = (int64_t)gp_sm_count_cached() * occ;   // everything resident at once
+  int64_t reducers = g_step.reducers;
+  const int64_t own_tiles = (a.n_tiles + p.n - 1) / p.n;
+  if (reducers > own_tiles) reducers = own_tiles;
+  if (reducers < 1) reducers = 1;
+  if (reducers > cap / 2) reducers = cap / 2 > 0 ? cap / 2 : 1;
+  int64_t workers = a.n_tiles;
+  if (workers > cap - reducers) workers = cap - reducers;
+  if (workers < 1) workers = 1;
+  p.reducers = (int)reducers;
+  kernel<<<(unsigned)(reducers + workers), kStepThreads, smem, st>>>(a, p, pk, up);
+  return gp_cuda_fail(cudaGetLastError(), "stepn_kernel launch");
+}
+
+template <class Upd, class B>
+int launch_stepn(const StepTables& a, const StepPeers& p, size_t smem, const PackOp& pk,
+                 const Upd& up, cudaStream_t st) {
+  if (p.mc_base) {
+    if (g_step.unroll >= 8) return launch_stepn_t<Upd, B, RedMc<B, 8>>(a, p, smem, pk, up, st);
+    if (g_step.unroll <= 2) return launch_stepn_t<Upd, B, RedMc<B, 2>>(a, p, smem, pk, up, st);
+    return launch_stepn_t<Upd, B, RedMc<B, 4>>(a, p, smem, pk, up, st);
+  }
+  switch (p.n) {
+    case 2: return launch_stepn_t<Upd, B, RedP2p<B, 2>>(a, p, smem, pk, up, st);
+    case 4: return launch_stepn_t<Upd, B, RedP2p<B, 4>>(a, p, smem, pk, up, st);
+    default: return launch_stepn_t<Upd, B, RedP2p<B, 8>>(a, p, smem, pk, up, st);
+  }
+}
+
+// what the step kernels cover; everything else stays on the pack / allreduce / update
+// launches (the host checks with gp_step_supported first)
+bool step_covers(int n_ranks, int buf_dtype, int layout_hint, double scale) {
+  if (n_ranks != 1 && n_ranks != 2 && n_ranks != 4 && n_ranks != 8) return false;
+  if (buf_dtype != GP_F32 && buf_dtype != GP_F16 && buf_dtype != GP_BF16) return false;
+  if (layout_hint != GP_F32) return false;
+  const ScaleArg s = make_scale(scale);
+  if (n_ranks == 1) return s.mode != 2;
+  return s.mode == 1;
+}
+
+template <class Upd>
+int step_dispatch(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, const int64_t* d_csum,
+                  const gp_seg_t* d_segs, int n_segs, int64_t n_elems, double scale, int layout_hint,
+                  Upd up, void* stream, const char* what) {
+  if (n_segs <= 0 || n_elems <= 0) return 0;
+  P2PComm* c = (P2PComm*)p2p_comm;
+  const int n_ranks = c ? c->n : 1;
+  if (!step_covers(n_ranks, buf_dtype, layout_hint, scale)) {
+    gp_set_error("%s: not covered by the one-launch step (ranks %d, buffer dtype %d, layout hint %d, "
+                 "scale %g)", what, n_ranks, buf_dtype, layout_hint, scale);
+    return GP_EINVAL;
+  }
+  PackOp pk;
+  pk.buffer = buffer;
+  pk.s = make_scale(1.0);
+  up.buffer = buffer;
+  up.s = make_scale(scale);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = 0;
+  if (!c) {
+    int64_t tile = g_step.tile1_elems;
+    const StepTables a = make_tables(d_csum, d_segs, n_segs, n_elems, tile, &smem);
+    switch (buf_dtype) {
+      case GP_F32: return launch_step1<Upd, float>(a, smem, pk, up, st);
+      case GP_F16: return launch_step1<Upd, __half>(a, smem, pk, up, st);
+      default: return launch_step1<Upd, __nv_bfloat16>(a, smem, pk, up, st);
+    }
+  }
+  if (c->step_tile_cap <= 0 || c->step_tile_elems <= 0) {
+    gp_set_error("%s: per-tile words not set (gp_p2p_set_step_words)", what);
+    return GP_EINVAL;
+  }
+  const StepTables a = make_tables(d_csum, d_segs, n_segs, n_elems, c->step_tile_elems, &smem);
+  if (a.n_tiles > c->step_tile_cap) {
+    gp_set_error("%s: %lld tiles exceed the capacity %lld of the per-tile words", what,
+                 (long long)a.n_tiles, (long long)c->step_tile_cap);
+    return GP_EINVAL;
+  }
+  StepPeers p;
+  for (int k = 0; k < kMaxRanks; ++k) {
+    p.words[k] = k < c->n ? c->step_words[k] : nullptr;
+    p.bufs[k] = k < c->n ? c->bufs[k] : nullptr;
+  }
+  p.mc_base = (char*)mc_ptr;
+  p.tile_cap = c->step_tile_cap;
+  p.rank = c->rank;
+  p.n = c->n;
+  p.reducers = 0;
+  p.timeout_ns = g_gp_peer_timeout_ns;
+  if (!mc_ptr) {
+    if (c->bufs[c->rank] != buffer) {
+      gp_set_error("%s: buffer is not the rank's registered packed buffer (gp_p2p_set_buffers)", what);
+      return GP_EINVAL;
+    }
+  }
+  p.epoch = ++c->step_epoch;
+  switch (buf_dtype) {
+    case GP_F32: return launch_stepn<Upd, float>(a, p, smem, pk, up, st);
+    case GP_F16: return launch_stepn<Upd, __half>(a, p, smem, pk, up, st);
+    default: return launch_stepn<Upd, __nv_bfloat16>(a, p, smem, pk, up, st);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gp_step_supported(int n_ranks, int buf_dtype, int layout_hint, double scale, int adam_flags) {
+  if (adam_flags & GP_ADAM_AMSGRAD) return 0;
+  return step_covers(n_ranks, buf_dtype, layout_hint, scale) ? 1 : 0;
+}
+
+size_t gp_step_words_bytes(int64_t tile_cap) { return (size_t)tile_cap * 2 * sizeof(uint32_t); }
+
+int gp_step_tile_elems(void) { return g_step.tile_elems; }
+
+// Collective (host side): `blocks[k]` is this process's mapping of rank k's ZEROED word
+// block of gp_step_words_bytes(tile_cap) bytes; restarts the step epoch.
+int gp_p2p_set_step_words(void* comm, void* const* blocks, int64_t tile_cap, int64_t tile_elems) {
+  P2PComm* c = (P2PComm*)comm;
+  if (!c || tile_cap <= 0 || tile_elems < 4096 || (tile_elems % 4096)) {
+    gp_set_error("gp_p2p_set_step_words: bad arguments (tile_cap %lld, tile_elems %lld)",
+                 (long long)tile_cap, (long long)tile_elems);
+    return GP_EINVAL;
+  }
+  for (int k = 0; k < c->n; ++k) c->step_words[k] = (uint32_t*)blocks[k];
+  c->step_tile_cap = tile_cap;
+  c->step_tile_elems = tile_elems;
+  c->step_epoch = 0;
+  return 0;
+}
+
+int gp_step_momentum_sgd(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype,
+                         const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t n_elems,
+                         double scale, double lr, double momentum, int write_grad, int layout_hint,
+                         void* stream) {
+  SgdOp<false> up;
+  up.lr = lr;
+  up.momentum = momentum;
+  up.write_grad = write_grad;
+  up.hooks = {nullptr, 0.0, 0.0};
+  return step_dispatch(p2p_comm, mc_ptr, buffer, buf_dtype, d_csum, d_segs, n_segs, n_elems, scale,
+                       layout_hint, up, stream, "gp_step_momentum_sgd");
+}
+
+int gp_step_adam(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, const int64_t* d_csum,
+                 const gp_seg_t* d_segs, int n_segs, int64_t n_elems, double scale, double alpha_t,
+                 double one_minus_beta1, double one_minus_beta2, double eps, double eta,
+                 double weight_decay_rate, double lower, double upper, int adam_flags,
+                 int write_grad, int layout_hint, void* stream) {
+  if (adam_flags & GP_ADAM_AMSGRAD) {
+    gp_set_error("gp_step_adam: AMSGrad is not covered by the one-launch step");
+    return GP_EINVAL;
+  }
+  AdamOp<false, false> up;
+  up.alpha_t = alpha_t; up.omb1 = one_minus_beta1; up.omb2 = one_minus_beta2; up.eps = eps;
+  up.eta = eta; up.wd = weight_decay_rate; up.lower = lower; up.upper = upper;
+  up.flags = adam_flags; up.write_grad = write_grad;
+  up.hooks = {nullptr, 0.0, 0.0};
+  return step_dispatch(p2p_comm, mc_ptr, buffer, buf_dtype, d_csum, d_segs, n_segs, n_elems, scale,
+                       layout_hint, up, stream, "gp_step_adam");
+}
+
+int gp_step_set_tuning(const char* key, int value) {
+  if (!key) return GP_EINVAL;
+  if (!strcmp(key, "tile_elems")) g_step.tile_elems = value < 4096 ? 4096 : value / 4096 * 4096;
+  else if (!strcmp(key, "reducers")) g_step.reducers = value < 1 ? 1 : value;
+  else if (!strcmp(key, "unroll")) g_step.unroll = value;
+  else if (!strcmp(key, "ctas_per_sm")) g_step.ctas_per_sm = value;
+  else if (!strcmp(key, "tile1_elems")) g_step.tile1_elems = value < 1024 ? 1024 : value / 1024 * 1024;
+  else if (!strcmp(key, "grid1")) g_step.grid1 = value;
+  else {
+    gp_set_error("gp_step_set_tuning: unknown key '%s'", key);
+    return GP_EINVAL;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -61,21 +61,13 @@ __device__ __forceinline__ int seg_seek(const int64_t* cs, int n, int j, int64_t
 //   template <class B, class P, int U, int SM> void vec(seg[U], e[U], act[U]) const
 //   template <class B, int SM> void scalar(const gp_seg_t&, int64_t e) const
 // B = buffer element type (per launch), P = parameter element type (per tile).
+// The CTA's share of the walk: every warp of the CTA takes warp tiles of the flat
+// range [lo, hi) (lo a multiple of 4; the kernels call this with whole-CTA control
+// flow, but there is no barrier inside).  `cs` is the cumulative-size table (shared
+// or global memory).
 template <class Op, class B, int U, int SM, int PT>
-__global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, const Op op) {
-  extern __shared__ int64_t s_csum[];
-  const int n = a.n_segs;
-  const int64_t lo = a.begin + (int64_t)blockIdx.x * a.per_cta;
-  const int64_t hi = (lo + a.per_cta < a.end) ? lo + a.per_cta : a.end;
-  if (lo >= hi) return;
-
-  const int64_t* cs = a.csum;
-  if (a.use_smem) {
-    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_csum[i] = a.csum[i];
-    __syncthreads();
-    cs = s_csum;
-  }
-
+__device__ __forceinline__ void walk_range(const int64_t* cs, const gp_seg_t* segs, int n,
+                                           int64_t lo, int64_t hi, const Op& op) {
   constexpr int WT = 32 * U * 4;  // elements per warp tile
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -101,12 +93,12 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t row = base + u * 128;
-      sg[u] = a.segs + jr;
+      sg[u] = segs + jr;
       e[u] = 0;
       act[u] = true;
       if (ok) {
         jr = seg_seek(cs, n, jr, row);
-        const gp_seg_t* g = a.segs + jr;
+        const gp_seg_t* g = segs + jr;
         const int k = Op::key(*g);
         if (u == 0) key0 = k;
         ok = (row + 128 <= cs[jr + 1]) && (g->flags & GP_SEG_VEC_OK) && k == key0 && k != GP_F64;
@@ -132,12 +124,29 @@ __global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, con
         const int64_t flat = base + (int64_t)k * 32 + lane;
         if (flat < hi) {
           js = seg_seek(cs, n, js, flat);
-          if constexpr (PT == GP_F32) op.template one<B, float, SM>(a.segs[js], flat - cs[js]);
-          else op.template scalar<B, SM>(a.segs[js], flat - cs[js]);
+          if constexpr (PT == GP_F32) op.template one<B, float, SM>(segs[js], flat - cs[js]);
+          else op.template scalar<B, SM>(segs[js], flat - cs[js]);
         }
       }
     }
   }
+}
+
+template <class Op, class B, int U, int SM, int PT>
+__global__ void __launch_bounds__(kMaxThreads) walk_kernel(const WalkArgs a, const Op op) {
+  extern __shared__ int64_t s_csum[];
+  const int n = a.n_segs;
+  const int64_t lo = a.begin + (int64_t)blockIdx.x * a.per_cta;
+  const int64_t hi = (lo + a.per_cta < a.end) ? lo + a.per_cta : a.end;
+  if (lo >= hi) return;
+
+  const int64_t* cs = a.csum;
+  if (a.use_smem) {
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_csum[i] = a.csum[i];
+    __syncthreads();
+    cs = s_csum;
+  }
+  walk_range<Op, B, U, SM, PT>(cs, a.segs, n, lo, hi, op);
 }
 
 // resident CTAs per SM of one instantiation (cached: the occupancy query is a

@@ -403,6 +403,48 @@ int gp_mc_allreduce(void* p2p_comm, void* mc, int dtype, int64_t offset_elems, i
                     void* stream);
 int gp_mc_set_tuning(int ctas, int threads, int unroll);
 
+/* ---------------------------------------------------------------- one-launch step
+ * The WHOLE per-step path of `_MultiNodeOptimizer.update`
+ * (chainermn/optimizers.py:17-33) as one kernel launch per rank: pack
+ * (_memory_utility.py:253-268, 289-358) -> sum over ranks
+ * (pure_nccl_communicator.py:180-182) -> 1/N (:183-189) -> unpack
+ * (_memory_utility.py:271-286, 361-429) -> update_core_gpu
+ * (chainer/optimizers/momentum_sgd.py:75-88, adam.py:224-332), flowing tile by tile
+ * through the packed buffer (csrc/gp_step.cu).  Results are identical to gp_pack +
+ * gp_p2p_allreduce / gp_mc_allreduce + gp_unpack_momentum_sgd / gp_unpack_adam.
+ *
+ *   p2p_comm  NULL: one rank (no exchange); else the gp_p2p_create handle of 2/4/8 ranks
+ *             whose per-tile words were set with gp_p2p_set_step_words
+ *   mc_ptr    NULL: peer-memory transport (the buffers of gp_p2p_set_buffers; sums in
+ *             rank order, bit-exact on every rank); else the MULTICAST address of
+ *             `buffer` (gp_mc_pointers): the NVSwitch adds the copies
+ *   buffer    this rank's packed buffer (unicast address), n_elems elements of
+ *             buf_dtype (float32 / float16 / bfloat16), capacity rounded up to 16 bytes
+ *   tables    as gp_unpack_momentum_sgd / gp_unpack_adam (ptr[0] = gradient: packed
+ *             from, and with write_grad the mean written back to); layout_hint must
+ *             be GP_F32 (all arrays float32); scale = 1/size
+ * gp_step_supported tells whether a configuration is covered (else use the separate
+ * launches).  Collective at N > 1: every rank launches the same step.
+ */
+int gp_step_supported(int n_ranks, int buf_dtype, int layout_hint, double scale, int adam_flags);
+int gp_step_momentum_sgd(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype,
+                         const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t n_elems,
+                         double scale, double lr, double momentum, int write_grad, int layout_hint,
+                         void* stream);
+int gp_step_adam(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, const int64_t* d_csum,
+                 const gp_seg_t* d_segs, int n_segs, int64_t n_elems, double scale, double alpha_t,
+                 double one_minus_beta1, double one_minus_beta2, double eps, double eta,
+                 double weight_decay_rate, double lower, double upper, int adam_flags,
+                 int write_grad, int layout_hint, void* stream);
+/* per-tile words of the N-rank step: [tile_cap "packed" counters | tile_cap "reduced"
+ * flags] (uint32) per rank, zeroed, shared through gp_ipc_*; tile_elems (a multiple of
+ * 4096, gp_step_tile_elems() is the tuned default) is fixed for the life of the words */
+size_t gp_step_words_bytes(int64_t tile_cap);
+int gp_step_tile_elems(void);
+int gp_p2p_set_step_words(void* p2p_comm, void* const* blocks, int64_t tile_cap, int64_t tile_elems);
+/* keys: tile_elems, reducers, unroll, ctas_per_sm (N ranks); tile1_elems, grid1 (one rank) */
+int gp_step_set_tuning(const char* key, int value);
+
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking
  * sweeps; defaults are the tuned values recorded in DESIGN.md. */
 int gp_set_tuning(const char* key, int value);

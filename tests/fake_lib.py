@@ -253,6 +253,54 @@ class FakeLib(object):
                 _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
         return 0
 
+    # -- one-launch step (csrc/gp_step.cu): same results as the separate launches -----
+    def gp_step_supported(self, n_ranks, buf_dtype, layout_hint, scale, adam_flags):
+        # the double covers the one-rank step only (no peer memory on the host)
+        return 1 if (n_ranks == 1 and buf_dtype in (6, 7, 9) and layout_hint == 7 and
+                     not (adam_flags & 1) and float(scale) == 1.0) else 0
+
+    def gp_step_tile_elems(self):
+        return 16384
+
+    def gp_step_words_bytes(self, cap):
+        return cap * 8
+
+    def gp_step_set_tuning(self, key, value):
+        self.tuning['step_' + (key.decode() if isinstance(key, bytes) else key)] = value
+        return 0
+
+    def gp_step_momentum_sgd(self, comm, mc_ptr, buffer, buf_dtype, d_csum, d_segs, n, n_elems,
+                             scale, lr, momentum, write_grad, layout_hint, stream):
+        assert comm is None and mc_ptr is None
+        self.calls.append(('gp_step_momentum_sgd', (buf_dtype, n, n_elems, scale, lr, momentum,
+                                                    write_grad)))
+        log = self.calls
+        self.calls = []
+        try:
+            self.gp_pack(buffer, buf_dtype, d_csum, d_segs, n, 0, n_elems, 1.0, layout_hint, stream)
+            self.gp_unpack_momentum_sgd(buffer, buf_dtype, d_csum, d_segs, n, 0, n_elems, scale, lr,
+                                        momentum, write_grad, layout_hint, stream)
+        finally:
+            self.calls = log
+        return 0
+
+    def gp_step_adam(self, comm, mc_ptr, buffer, buf_dtype, d_csum, d_segs, n, n_elems, scale,
+                     alpha_t, omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad,
+                     layout_hint, stream):
+        assert comm is None and mc_ptr is None
+        self.calls.append(('gp_step_adam', (buf_dtype, n, n_elems, scale, alpha_t, flags,
+                                            write_grad)))
+        log = self.calls
+        self.calls = []
+        try:
+            self.gp_pack(buffer, buf_dtype, d_csum, d_segs, n, 0, n_elems, 1.0, layout_hint, stream)
+            self.gp_unpack_adam(buffer, buf_dtype, d_csum, d_segs, n, 0, n_elems, scale, alpha_t,
+                                omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad,
+                                layout_hint, stream)
+        finally:
+            self.calls = log
+        return 0
+
     # -- hooks (csrc/gp_hooks.cu, gp_sgd_hooks.cu, gp_adam_hooks.cu) --------------
     @staticmethod
     def _apply_hooks(g, p, hooks_addr, pdt):

@@ -1,6 +1,7 @@
-"""The reference arm of bench.py (`--impl reference`: the oracle port of the naive
-communicator step on host cores) keeps the JSON contract of the driver, at one rank
-and at N ranks."""
+"""The reference arm of bench.py (`--impl reference`: the unmodified chainermn naive
+communicator + chainer update_core_cpu from baseline/_ref when that install is present,
+else the oracle port, on host cores) keeps the JSON contract of the driver, at one rank
+and at N ranks, and prints the same `config` object as the B200 arm would."""
 import json
 import os
 import subprocess
@@ -15,10 +16,11 @@ KEYS = {'impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_
         'e2e'}
 
 
+@pytest.mark.parametrize('kind', ['auto', 'port'])
 @pytest.mark.parametrize('n', [1, 2])
-def test_reference_arm_line(n):
+def test_reference_arm_line(n, kind):
     cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', str(n),
-           '--steps', '2', '--warmup', '1', '--workload', 'mnist_mlp']
+           '--steps', '2', '--warmup', '1', '--workload', 'mnist_mlp', '--reference-kind', kind]
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
     out = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True, timeout=600)
@@ -29,7 +31,18 @@ def test_reference_arm_line(n):
     assert KEYS <= set(line)
     assert line['impl'] == 'reference' and line['n_gpus'] == n and line['vs_baseline'] is None
     assert line['value'] > 0 and line['ms_per_step'] > 0 and line['higher_is_better'] is True
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == n
+    have_ref = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'chainermn'))
+    want_kind = 'reference' if (kind == 'auto' and have_ref) else 'port'
+    assert line['cpu_baseline']['kind'] == want_kind and line['cpu_baseline']['cores'] == n
+    assert line['steps'] == 2 and line['warmup'] == 1          # exactly what was asked for
+    # the same `config` the B200 arm prints for these flags
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(workload='mnist_mlp', allreduce_dtype='float32', no_write_grad=False,
+                              zero_embedding_rows=0.0)
+    _, sizes = bench.workload_sizes('mnist_mlp')
+    assert line['config'] == bench.make_config(args, 'adam', n, sizes)
     assert line['cpu_baseline']['value'] == line['value'] == line['e2e']['value']
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in line['config'] and 'model' not in line['config']

@@ -34,6 +34,7 @@ def test_multi_gpu_path(world_size, transport):
     env = dict(os.environ)
     env['CHAINER_B200_P2P'] = '0' if transport == 'nccl' else '1'
     env['CHAINER_B200_MULTICAST'] = '1' if transport == 'multicast' else '0'
+    env['CHAINER_B200_PEER_TIMEOUT_S'] = '60'      # a dead peer fails the test, not the box
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node', str(world_size), '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', '_dist_gpu_worker.py')]
@@ -45,6 +46,8 @@ def test_multi_gpu_path(world_size, transport):
     for line in out.stdout.splitlines():
         if line.startswith('MNBN statistics exchange'):
             print(line)
+    if transport != 'nccl':
+        assert 'ONE-LAUNCH STEP OK' in out.stdout
     if transport == 'multicast':
         if 'MULTICAST UNSUPPORTED' in out.stdout:
             pytest.skip([ln for ln in out.stdout.splitlines() if 'MULTICAST UNSUPPORTED' in ln][0])
