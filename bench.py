@@ -972,7 +972,7 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
     import chainer_b200
     from chainer_b200.core.link import link_from_named_arrays
     torch.manual_seed(7)
-    net = torchvision.models.resnet50(weights=None).cuda().to(memory_format=torch.channels_last)
+    net = torchvision.models.resnet50(weights=None).cuda()      # contiguous (NCHW) parameters
     net.train()
     x = torch.randn(batch, 3, 224, 224, device='cuda').to(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (batch,), device='cuda')
@@ -986,7 +986,7 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
         return loss
 
     out = {'model': 'torchvision resnet50 stand-in ({} tensors, {} parameters), batch {}/GPU, '
-                    'synthetic 224x224, bf16 autocast forward/backward (channels_last), fp32 '
+                    'synthetic 224x224 (channels_last input), bf16 autocast forward/backward, fp32 '
                     'parameters, gradients and MomentumSGD state'.format(len(named), n_params, batch),
            'batch_per_gpu': batch, 'steps': steps}
 

@@ -68,6 +68,7 @@ class ParamsData(object):
         else:
             segs['buf_off'] = np.asarray(buf_offsets, dtype=np.int64)
         self._hint4 = self._hint8 = False
+        self.all_float32 = False
         self.n_params = n_params
         self.n_elems = int(csum[n_params])
         self.attr_name = attr_name
@@ -115,6 +116,7 @@ class ParamsData(object):
         # (of 4 when the packed buffer is a 4-byte type too)
         f32 = bool(np.all(segs['dtype0'] == _lib.GP_F32) and np.all(segs['dtype1'] == _lib.GP_F32))
         al16 = bool(np.all(segs['ptr'] % np.uint64(16) == 0))
+        self.all_float32 = f32        # what the one-launch step needs (any alignment)
         self._hint4 = f32 and al16 and bool(np.all(csum % 4 == 0) and np.all(segs['buf_off'] % 4 == 0))
         self._hint8 = self._hint4 and bool(np.all(csum % 8 == 0) and np.all(segs['buf_off'] % 8 == 0))
 

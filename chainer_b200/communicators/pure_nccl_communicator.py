@@ -750,7 +750,7 @@ class _FusedPlan(object):
             want = _step_enabled_by_env()
         if not want or key[0] not in ('momentum_sgd', 'adam'):
             return False
-        hint = t.layout_hint(dtype)
+        hint = _lib.GP_F32 if t.all_float32 else 0     # no alignment requirement here
         adam_flags = key[9] if key[0] == 'adam' else 0
         if not lib.gp_step_supported(comm.size, buf_id, hint, scale, adam_flags):
             return False

@@ -71,7 +71,8 @@ struct AdamOp {
     P *pp[U], *pm[U], *pv[U], *ph[AMS ? U : 1], *pg[U];  // resolved once, before any store
   };
 
-  template <class B, class P, int U>
+  // WITH_BUF false: the caller supplies r.rb (one-launch step at one rank, gp_step.cu)
+  template <class B, class P, int U, bool WITH_BUF = true>
   __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                        const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
@@ -82,7 +83,7 @@ struct AdamOp {
         r.pv[u] = mptr<P>(seg[u]->ptr[3]) + e[u];
         r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
         if constexpr (AMS) r.ph[u] = mptr<P>(seg[u]->ptr[4]) + e[u];
-        r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
+        if constexpr (WITH_BUF) r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
         r.rp[u] = ld4(r.pp[u]);
         r.rm[u] = ld4(r.pm[u]);
         r.rv[u] = ld4(r.pv[u]);

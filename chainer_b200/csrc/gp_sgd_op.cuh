@@ -47,7 +47,8 @@ struct SgdOp {
     P *pp[U], *pv[U], *pg[U];  // resolved once, before any store (no table re-reads)
   };
 
-  template <class B, class P, int U>
+  // WITH_BUF false: the caller supplies r.rb (one-launch step at one rank, gp_step.cu)
+  template <class B, class P, int U, bool WITH_BUF = true>
   __device__ __forceinline__ void load(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
                                        const bool (&act)[U], Regs<B, P, U>& r) const {
 #pragma unroll
@@ -56,7 +57,7 @@ struct SgdOp {
         r.pp[u] = mptr<P>(seg[u]->ptr[1]) + e[u];
         r.pv[u] = mptr<P>(seg[u]->ptr[2]) + e[u];
         r.pg[u] = mptr<P>(seg[u]->ptr[0]) + e[u];
-        r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
+        if constexpr (WITH_BUF) r.rb[u] = ld4_stream(grad_src<B>(*seg[u], e[u]));
         r.rp[u] = ld4(r.pp[u]);
         r.rv[u] = ld4(r.pv[u]);
       }

@@ -14,9 +14,8 @@
 // The packed buffer is cut into TILES of `tile_elems` elements (a multiple of 4096:
 // 16-byte vectors for every buffer dtype, whole walker tiles).
 //
-// One rank (gp_step*, comm == NULL): a CTA packs tile t and, after a CTA barrier,
-// runs the fused update on the same tile: the packed values are read back from
-// L1/L2, never from HBM, and there is no kernel boundary between the stages.
+// One rank (gp_step*, comm == NULL): pack and update are fused at the register level
+// (PackUpd below): the packed buffer is written once and never read back.
 //
 // N ranks (2, 4, 8 on one NVSwitch box): tile t is OWNED by rank t % N.
 //   worker CTAs   pack their tiles in tile order; after each tile one
@@ -66,19 +65,48 @@ __device__ __forceinline__ const int64_t* stage_csum(const StepTables& a, int64_
 }
 
 // ------------------------------------------------------------------ one rank --
-template <class Upd, class B, int SM>
-__global__ void __launch_bounds__(kStepThreads) step1_kernel(const StepTables a, const PackOp pk,
-                                                            const Upd up) {
-  extern __shared__ int64_t s_csum[];
-  const int64_t* cs = stage_csum(a, s_csum);
-  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-    const int64_t lo = t * a.tile_elems;
-    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
-    gpw::walk_range<PackOp, B, 4, 0, GP_F32>(cs, a.segs, a.n_segs, lo, hi, pk);
-    __syncthreads();   // the CTA's packed values are visible to all its threads
-    gpw::walk_range<Upd, B, Upd::kDefaultUnroll, SM, GP_F32>(cs, a.segs, a.n_segs, lo, hi, up);
+// Pack and update fused at the REGISTER level: a warp loads its gradient vectors, casts
+// them to the buffer type, stores them into the packed buffer (it stays observable as
+// `gpu_buffer_a`, bit-exact with gp_pack) and feeds the same registers to the fused
+// update -- the packed buffer is written once and never read back.  An ordinary walker
+// launch (gp_walk.cuh) with this combined op.
+template <class Upd>
+struct PackUpd {
+  static constexpr int kMaxUnroll = Upd::kMaxUnroll;
+  static constexpr int kDefaultUnroll = Upd::kDefaultUnroll;
+  Upd up;       // up.buffer: the packed buffer; up.s: the 1/size scale
+  ScaleArg s;   // == up.s (the launcher reads op.s.mode)
+
+  static __device__ __forceinline__ int key(const gp_seg_t& g) { return Upd::key(g); }
+
+  template <class B, class P, int U, int SM>
+  __device__ __forceinline__ void vec(const gp_seg_t* const (&seg)[U], const int64_t (&e)[U],
+                                      const bool (&act)[U]) const {
+    using CP = typename Carrier<P>::type;
+    typename Upd::template Regs<B, P, U> r;
+    Raw4<P> rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (act[u]) rg[u] = ld4_stream(cptr<P>(seg[u]->ptr[0]) + e[u]);
+    up.template load<B, P, U, false>(seg, e, act, r);
+    B* buf = reinterpret_cast<B*>(const_cast<void*>(up.buffer));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (act[u]) {
+        CP x[4];
+        unpack4(rg[u], x);
+        r.rb[u] = pack4<B, CP>(x);                       // the cast of gp_pack (RN)
+        st4(buf + seg[u]->buf_off + e[u], r.rb[u]);
+      }
+    up.template finish<B, P, U, SM>(seg, e, act, r);
   }
-}
+  template <class B, class P, int SM>
+  __device__ __forceinline__ void one(const gp_seg_t& g, int64_t e) const {
+    B* buf = reinterpret_cast<B*>(const_cast<void*>(up.buffer));
+    buf[g.buf_off + e] = from_carrier<B>(to_carrier(cptr<P>(g.ptr[0])[e]));
+    up.template one<B, P, SM>(g, e);                     // reads it back (same thread)
+  }
+};
 
 // ------------------------------------------------------------------- N ranks --
 struct StepPeers {
@@ -278,10 +306,8 @@ struct StepTuning {
   int reducers;     // reducer CTAs per rank (N ranks)
   int unroll;       // MC transport: 16-byte vectors per thread and pipeline stage (4, 8)
   int ctas_per_sm;  // cap of resident CTAs per SM (0: the occupancy)
-  int tile1_elems;  // one rank: tile size
-  int grid1;        // one rank: 0 = one CTA per tile, else persistent CTAs per SM
 };
-StepTuning g_step = {16384, 32, 4, 4, 8192, 0};
+StepTuning g_step = {16384, 32, 4, 4};
 
 template <class K>
 int occupancy(K kernel, size_t smem) {
@@ -309,21 +335,30 @@ StepTables make_tables(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs
 }
 
 template <class Upd, class B>
-int launch_step1(const StepTables& a, size_t smem, const PackOp& pk, const Upd& up, cudaStream_t st) {
-  auto launch = [&](auto kernel) {
-    int64_t grid = a.n_tiles;
-    if (g_step.grid1 > 0) {
-      int occ = occupancy(kernel, smem);
-      if (g_step.grid1 < occ) occ = g_step.grid1;
-      const int64_t cap = (int64_t)gp_sm_count_cached() * occ;
-      if (grid > cap) grid = cap;
-    }
-    if (grid > 0x7fffffff) grid = 0x7fffffff;
-    kernel<<<(unsigned)grid, kStepThreads, smem, st>>>(a, pk, up);
-    return gp_cuda_fail(cudaGetLastError(), "step1_kernel launch");
-  };
-  if (up.s.mode == 0) return launch(step1_kernel<Upd, B, 0>);
-  return launch(step1_kernel<Upd, B, 1>);
+int launch_step1(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t n_elems,
+                 const Upd& up, cudaStream_t st, const char* what) {
+  PackUpd<Upd> op;
+  op.up = up;
+  op.s = up.s;
+  const GpTuning& t = g_gp_tuning;
+  int threads = t.threads < 32 ? 32 : (t.threads > gpw::kMaxThreads ? gpw::kMaxThreads : t.threads);
+  threads &= ~31;
+  gpw::WalkArgs a;
+  a.csum = d_csum;
+  a.segs = d_segs;
+  a.n_segs = n_segs;
+  a.use_smem = n_segs <= gpw::kMaxSmemSegs;
+  a.begin = 0;
+  a.end = n_elems;
+  a.per_cta = 0;
+  const size_t smem = a.use_smem ? (size_t)(n_segs + 1) * sizeof(int64_t) : 0;
+  const bool u4 = t.unroll >= 4;
+  if (up.s.mode == 0) {
+    if (u4) return gpw::launch_u<PackUpd<Upd>, B, 4, 0, GP_F32>(a, op, threads, smem, st, what);
+    return gpw::launch_u<PackUpd<Upd>, B, 2, 0, GP_F32>(a, op, threads, smem, st, what);
+  }
+  if (u4) return gpw::launch_u<PackUpd<Upd>, B, 4, 1, GP_F32>(a, op, threads, smem, st, what);
+  return gpw::launch_u<PackUpd<Upd>, B, 2, 1, GP_F32>(a, op, threads, smem, st, what);
 }
 
 template <class Upd, class B, class Red>
@@ -392,12 +427,10 @@ int step_dispatch(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, con
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = 0;
   if (!c) {
-    int64_t tile = g_step.tile1_elems;
-    const StepTables a = make_tables(d_csum, d_segs, n_segs, n_elems, tile, &smem);
     switch (buf_dtype) {
-      case GP_F32: return launch_step1<Upd, float>(a, smem, pk, up, st);
-      case GP_F16: return launch_step1<Upd, __half>(a, smem, pk, up, st);
-      default: return launch_step1<Upd, __nv_bfloat16>(a, smem, pk, up, st);
+      case GP_F32: return launch_step1<Upd, float>(d_csum, d_segs, n_segs, n_elems, up, st, what);
+      case GP_F16: return launch_step1<Upd, __half>(d_csum, d_segs, n_segs, n_elems, up, st, what);
+      default: return launch_step1<Upd, __nv_bfloat16>(d_csum, d_segs, n_segs, n_elems, up, st, what);
     }
   }
   if (c->step_tile_cap <= 0 || c->step_tile_elems <= 0) {
@@ -501,8 +534,6 @@ int gp_step_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "reducers")) g_step.reducers = value < 1 ? 1 : value;
   else if (!strcmp(key, "unroll")) g_step.unroll = value;
   else if (!strcmp(key, "ctas_per_sm")) g_step.ctas_per_sm = value;
-  else if (!strcmp(key, "tile1_elems")) g_step.tile1_elems = value < 1024 ? 1024 : value / 1024 * 1024;
-  else if (!strcmp(key, "grid1")) g_step.grid1 = value;
   else {
     gp_set_error("gp_step_set_tuning: unknown key '%s'", key);
     return GP_EINVAL;

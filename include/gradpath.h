@@ -442,7 +442,8 @@ int gp_step_adam(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, cons
 size_t gp_step_words_bytes(int64_t tile_cap);
 int gp_step_tile_elems(void);
 int gp_p2p_set_step_words(void* p2p_comm, void* const* blocks, int64_t tile_cap, int64_t tile_elems);
-/* keys: tile_elems, reducers, unroll, ctas_per_sm (N ranks); tile1_elems, grid1 (one rank) */
+/* keys: tile_elems, reducers, unroll, ctas_per_sm (N-rank step; the one-rank step is a walker
+ * launch and follows gp_set_tuning) */
 int gp_step_set_tuning(const char* key, int value);
 
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking

@@ -1,5 +1,6 @@
 """GPU parity tests of the one-launch step kernels (csrc/gp_step.cu) at world size 1:
-pack -> fused update in ONE kernel, through the C-ABI, BIT-EXACT against the NumPy
+pack -> fused update in ONE kernel (fused at the register level: the packed buffer is
+written once and never read back), through the C-ABI, BIT-EXACT against the NumPy
 oracle (pack layout and casts, the 1/N rounding sequence, MomentumSGD / Adam
 arithmetic) and therefore against the separate launches.  The N-rank kernels are
 covered by tests/test_multi_gpu.py (tests/_dist_gpu_worker.py).
@@ -26,17 +27,20 @@ def _torch_dt(dtype):
     return {'float32': torch.float32, 'float16': torch.float16, 'bfloat16': torch.bfloat16}[dtype]
 
 
-@pytest.fixture(params=[(8192, 0), (1024, 0), (65536, 2), (4096, 1)],
-                ids=['tile8192', 'tile1024', 'tile65536-persistent2', 'tile4096-persistent1'])
+@pytest.fixture(params=[(256, 0, 0), (256, 4, 0), (128, 2, 1), (512, 4, 1)],
+                ids=['default', 't256u4', 't128u2-persistent', 't512u4-persistent'])
 def step_tuning(request):
+    """The one-rank step is a walker launch: (threads, unroll, persistent) of gp_set_tuning."""
     from chainer_b200 import _lib
     lib = _lib.get()
-    tile, grid = request.param
-    lib.gp_step_set_tuning(b'tile1_elems', tile)
-    lib.gp_step_set_tuning(b'grid1', grid)
+    threads, unroll, persistent = request.param
+    lib.gp_set_tuning(b'threads', threads)
+    lib.gp_set_tuning(b'unroll', unroll)
+    lib.gp_set_tuning(b'persistent', persistent)
     yield request.param
-    lib.gp_step_set_tuning(b'tile1_elems', 8192)
-    lib.gp_step_set_tuning(b'grid1', 0)
+    lib.gp_set_tuning(b'threads', 256)
+    lib.gp_set_tuning(b'unroll', 0)
+    lib.gp_set_tuning(b'persistent', 0)
 
 
 @pytest.mark.parametrize('buf_dtype', ['float32', 'float16', 'bfloat16'])
@@ -66,7 +70,7 @@ def test_step1_momentum_sgd_bit_exact(buf_dtype, sizes, scale_ranks, write_grad,
         params = [P(data=d_p[i], grad=d_g[i]) for i in range(len(sizes))]
         pd = mu.ParamsData(params, 'grad', False,
                            extra_ptrs=[(d_p[i], [d_v[i]]) for i in range(len(sizes))])
-        assert pd.layout_hint(bdt) == 7
+        assert pd.all_float32
         lib.gp_step_momentum_sgd(None, None, buf.data_ptr(), dev.dtype_id(bdt), pd.d_csum,
                                  pd.d_segs, pd.n_params, n, 1.0 / scale_ranks, lr, mom,
                                  write_grad, 7, 0)
