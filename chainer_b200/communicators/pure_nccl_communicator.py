@@ -584,27 +584,33 @@ class _FusedPlan(object):
         """Device tables for the CURRENT gradient arrays.
 
         Chainer reallocates gradients every step (cleargrads), frameworks with
-        persistent gradient buffers do not, and benchmarks rotate a few sets: the
-        tables are cached per tuple of gradient array OBJECTS (the cache holds
-        references, so ids cannot be recycled), up to four sets, each with its own
-        device copy.  A hit costs one tuple of ids; a miss re-reads the pointers,
-        validates new arrays like ParamsData does and uploads one table.
+        persistent gradient buffers do not, and benchmarks rotate a few sets.  The
+        tables are cached per tuple of gradient ADDRESSES -- what the kernels consume,
+        so a key can never go stale and the cache holds no reference to any array (no
+        old gradient set is kept alive) -- up to four sets, each with its own device
+        copy.  A hit costs one tuple of addresses; a miss validates the new arrays like
+        ParamsData does and uploads one table.
         """
         params = self.params
-        # the gradients are held by their parameters, so the ids are those of live objects
-        ids = tuple(map(id, map(_GET_GRAD, params)))
-        if _NONE_ID in ids:
+        grads = list(map(_GET_GRAD, params))
+        try:
+            key = _dev.ptr_key(grads)
+        except ValueError:
+            if not any(g is None for g in grads):
+                raise
             for p in params:
                 if p.grad is None:
                     p.grad = _dev.zeros_like(p.data)         # zero_fill
-            ids = tuple(map(id, map(_GET_GRAD, params)))
-        ent = self.cache.get(ids)
-        if ent is not None:
+            grads = list(map(_GET_GRAD, params))
+            key = _dev.ptr_key(grads)
+        # (the dtype of a gradient equals its parameter's -- checked on a miss; an array
+        # of another dtype at a cached address is caught by this probe of both ends)
+        probe = (grads[0].dtype, grads[-1].dtype) if grads else None
+        ent = self.cache.get(key)
+        if ent is not None and ent.probe == probe:
             if len(self.cache) > 1:
-                self.cache.move_to_end(ids)
+                self.cache.move_to_end(key)
             return ent
-        grads = [p.grad for p in params]
-        ptrs = []
         for i, g in enumerate(grads):
             dt = _dev.array_dtype(g)
             if isinstance(dt, str) or dt != self.dtypes[i]:
@@ -615,14 +621,15 @@ class _FusedPlan(object):
             if _dev.array_size(g) != self.sizes[i]:
                 raise ValueError('gradient of size {} for a parameter of size {}'.format(
                     _dev.array_size(g), self.sizes[i]))
-            ptrs.append(_dev.device_ptr(g))
-        ptrs = np.asarray(ptrs, dtype=np.uint64)
-        if len(self.cache) >= 4:
-            _, ent = self.cache.popitem(last=False)          # recycle the oldest set's tables
-        else:
-            ent = _TableSet(self)
-        ent.update(ptrs, grads, stream)
-        self.cache[ids] = ent
+            _dev.device_ptr(g)                               # contiguity / device checks
+        ptrs = np.asarray(key, dtype=np.uint64)
+        if ent is None:
+            if len(self.cache) >= 4:
+                _, ent = self.cache.popitem(last=False)      # recycle the oldest set's tables
+            else:
+                ent = _TableSet(self)
+        ent.update(ptrs, probe, stream)
+        self.cache[key] = ent
         return ent
 
     def run(self, stream):
@@ -786,7 +793,6 @@ def _step_enabled_by_env():
     return os.environ.get('CHAINER_B200_STEP', '1') not in ('0', '', 'false', 'False')
 
 
-_NONE_ID = id(None)
 _GET_GRAD = operator.attrgetter('grad')
 
 
@@ -799,10 +805,10 @@ class _TableSet(object):
         self.groups = []
         for rep, idx, sub in plan.groups:
             self.groups.append((rep, idx, self.pd if idx is None else sub.clone()))
-        self.grads = None
+        self.probe = None
 
-    def update(self, ptrs, grads, stream):
-        self.grads = grads                       # keep the arrays (and their ids) alive
+    def update(self, ptrs, probe, stream):
+        self.probe = probe
         self.pd.set_ptr0(ptrs, stream)
         for _, idx, sub in self.groups:
             if idx is not None:

@@ -53,10 +53,17 @@ def update(opt):
             rule._check_eps(np.float32 if ddt == np.float16 else ddt.type)
         key = (ddt.str,) + rule.fused_key()
         groups.setdefault(key, []).append(p)
-    for key, plist in groups.items():
+    # one DeviceTable (a ring of pinned staging slots + device copies) per launch group,
+    # reused every step: no per-step cudaHostAlloc / cudaMalloc / cudaFree
+    tables = getattr(opt, '_mt_tables', None)
+    if tables is None:
+        tables = opt._mt_tables = []
+    for gi, (key, plist) in enumerate(groups.items()):
         extra = [(p.data, [p.update_rule.state[k] for k in p.update_rule.state_names])
                  for p in plist]
-        pd = _memory_utility.ParamsData(plist, 'grad', False, extra_ptrs=extra)
+        while len(tables) <= gi:
+            tables.append(_memory_utility.DeviceTable())
+        pd = _memory_utility.ParamsData(plist, 'grad', False, extra_ptrs=extra, table=tables[gi])
         dt_id = _dev.dtype_id(np.dtype(key[0]))
         k = key[1:]
         if k[0] == 'momentum_sgd':
@@ -71,5 +78,4 @@ def update(opt):
             lib.gp_unpack_adam(None, dt_id, pd.d_csum, pd.d_segs, pd.n_params, 0, pd.n_elems, 1.0,
                                k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], k[9], 0,
                                pd.layout_hint(np.dtype(key[0])), 0)
-        opt._mt_keep = getattr(opt, '_mt_keep', [])[-3:] + [pd]   # tables stay alive while queued
     return True

@@ -15,6 +15,7 @@ unsupported module (``_memory_utility.py:50-52``) -- except when the test-suite
 has swapped in its host-memory double of the C library (``_lib.set_backend_for_testing``).
 """
 import ctypes
+import operator
 
 import numpy as np
 
@@ -90,17 +91,30 @@ def dtype_itemsize(dtype):
     return np.dtype(dtype).itemsize
 
 
+_DATA_PTR = operator.methodcaller('data_ptr')
+
+
+def ptr_key(arrays):
+    """Tuple of the raw addresses of `arrays` -- the identity of a gradient set as the
+    kernels see it.  One C call per torch tensor (no validation: callers validate a set
+    the first time they see it); the generic route otherwise."""
+    try:
+        return tuple(map(_DATA_PTR, arrays))
+    except AttributeError:
+        return tuple(device_ptr(a) for a in arrays)
+
+
 def device_ptr(a):
     """Raw device address of `a` (int)."""
-    data = getattr(a, 'data', None)
-    if data is not None and hasattr(data, 'ptr'):        # cupy / DeviceArray
-        return int(data.ptr)
-    if is_torch(a):
+    if is_torch(a):                                      # (first: `tensor.data` is not free)
         if not a.is_cuda and not _lib.get().accepts_host_pointers:
             raise ValueError('{} is not on a CUDA device'.format(type(a)))
         if not a.is_contiguous():
             raise ValueError('non-contiguous array')
         return int(a.data_ptr())
+    data = getattr(a, 'data', None)
+    if data is not None and hasattr(data, 'ptr'):        # cupy / DeviceArray
+        return int(data.ptr)
     cai = getattr(a, '__cuda_array_interface__', None)
     if cai is not None:
         return int(cai['data'][0])

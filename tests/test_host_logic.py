@@ -21,7 +21,11 @@ from tests.helpers import assert_bits_equal
 
 
 @pytest.fixture
-def fake():
+def fake(monkeypatch):
+    """The oracle-backed double of the library.  The tests below assert on the names of
+    the SEPARATE launches (gp_pack / gp_unpack_*), so the one-launch step is switched off
+    here; test_one_launch_step_* cover it."""
+    monkeypatch.setenv('CHAINER_B200_STEP', '0')
     f, prev = fake_lib.install()
     _control_plane.reset_world()
     yield f
@@ -788,3 +792,55 @@ def test_batch_normalization_link_and_create_mnbn_model(fake):
     y4 = net.bn0(x.detach(), train=False)
     assert y3.shape == y4.shape
     comm.finalize()
+
+
+@pytest.mark.parametrize('opt_name', ['momentum_sgd', 'adam'])
+@pytest.mark.parametrize('adt', [None, np.float16])
+def test_one_launch_step_equals_separate_launches(fake, monkeypatch, opt_name, adt):
+    """With the one-launch step enabled (the default) update() issues ONE library launch
+    (gp_step_*) and leaves the same bits as pack + fused update; configurations it does
+    not cover (hooks, mixed dtypes) keep the separate launches."""
+    results = []
+    for use_step in ('1', '0'):
+        monkeypatch.setenv('CHAINER_B200_STEP', use_step)
+        comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=adt)
+        model = _model_with_values()
+        actual = chainer_b200.MomentumSGD(lr=0.1, momentum=0.9) if opt_name == 'momentum_sgd' \
+            else chainer_b200.Adam(alpha=0.01)
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+        opt.setup(model)
+        _set_grads(model, 1)
+        opt.update()
+        for step in range(1, 4):
+            _set_grads(model, 10 + step)
+            fake.calls[:] = []
+            opt.update()
+            names = [c[0] for c in fake.calls]
+            if use_step == '1':
+                assert names == ['gp_step_' + opt_name], names
+            else:
+                assert 'gp_pack' in names and not any(n.startswith('gp_step') for n in names)
+            assert actual.t == step
+        results.append([(n, p.data.copy(), p.grad.copy()) for n, p in sorted(model.namedparams())
+                        if p.data is not None])
+    for (n, d1, g1), (_, d0, g0) in zip(*results):
+        assert_bits_equal(d1, d0, n)
+        assert_bits_equal(g1, g0, n)
+
+
+def test_one_launch_step_not_taken_with_hooks(fake, monkeypatch):
+    from chainer_b200 import optimizer_hooks as H
+    monkeypatch.setenv('CHAINER_B200_STEP', '1')
+    comm = chainer_b200.create_communicator('pure_nccl')
+    model = _model_with_values()
+    actual = chainer_b200.MomentumSGD(lr=0.1, momentum=0.9)
+    actual_opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    actual_opt.setup(model)
+    actual.add_hook(H.WeightDecay(0.01))
+    _set_grads(model, 1)
+    actual_opt.update()
+    _set_grads(model, 2)
+    fake.calls[:] = []
+    actual_opt.update()
+    names = [c[0] for c in fake.calls]
+    assert 'gp_unpack_momentum_sgd_hooked' in names and 'gp_pack' in names
