@@ -228,28 +228,56 @@ __device__ __forceinline__ void st_sys(uint4* p, const uint4& v) {
 }
 template <class B, int N>
 struct RedP2p {
-  static __device__ __forceinline__ void run(const StepPeers& p, int64_t v0, int64_t v1) {
-    constexpr int UN = N >= 4 ? 2 : 4;
-    for (int64_t i = v0 + threadIdx.x; i < v1; i += (int64_t)kStepThreads * UN) {
-      uint4 x[UN][N];
+  // N * UN vector loads in flight per thread and pipeline stage
+  static constexpr int UN = N >= 8 ? 1 : 2;
+  static __device__ __forceinline__ void load(uint4 (&x)[UN][N], const StepPeers& p, int64_t i,
+                                              int64_t v1) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int64_t v = i + (int64_t)u * kStepThreads;
-        if (v < v1) {
+    for (int u = 0; u < UN; ++u) {
+      const int64_t v = i + (int64_t)u * kStepThreads;
+      if (v < v1) {
 #pragma unroll
-          for (int k = 0; k < N; ++k) x[u][k] = ld_sys(reinterpret_cast<const uint4*>(p.bufs[k]) + v);
-        }
+        for (int k = 0; k < N; ++k) x[u][k] = ld_sys(reinterpret_cast<const uint4*>(p.bufs[k]) + v);
       }
+    }
+  }
+  static __device__ __forceinline__ void store(const uint4 (&x)[UN][N], const StepPeers& p,
+                                               int64_t i, int64_t v1) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int64_t v = i + (int64_t)u * kStepThreads;
-        if (v < v1) {
-          uint4 acc = x[u][0];
+    for (int u = 0; u < UN; ++u) {
+      const int64_t v = i + (int64_t)u * kStepThreads;
+      if (v < v1) {
+        uint4 acc = x[u][0];
 #pragma unroll
-          for (int k = 1; k < N; ++k) Vec16<B>::add(acc, x[u][k]);
+        for (int k = 1; k < N; ++k) Vec16<B>::add(acc, x[u][k]);
 #pragma unroll
-          for (int k = 0; k < N; ++k) st_sys(reinterpret_cast<uint4*>(p.bufs[k]) + v, acc);
-        }
+        for (int k = 0; k < N; ++k) st_sys(reinterpret_cast<uint4*>(p.bufs[k]) + v, acc);
+      }
+    }
+  }
+  static __device__ __forceinline__ void run(const StepPeers& p, int64_t v0, int64_t v1) {
+    constexpr int64_t adv = (int64_t)kStepThreads * UN;
+    int64_t i = v0 + threadIdx.x;
+    if (i >= v1) return;
+    if constexpr (N >= 4) {
+      // 4 / 8 peers: N loads per vector are already a deep queue; no second stage
+      for (; i < v1; i += adv) {
+        uint4 x[UN][N];
+        load(x, p, i, v1);
+        store(x, p, i, v1);
+      }
+    } else {
+      uint4 x[UN][N], y[UN][N];
+      load(x, p, i, v1);
+      while (true) {
+        load(y, p, i + adv, v1);
+        store(x, p, i, v1);
+        i += adv;
+        if (i >= v1) break;
+        load(x, p, i + adv, v1);
+        store(y, p, i, v1);
+        i += adv;
+        if (i >= v1) break;
       }
     }
   }
@@ -303,11 +331,12 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
 // ------------------------------------------------------------------ launching --
 struct StepTuning {
   int tile_elems;   // multiple of 4096
-  int reducers;     // reducer CTAs per rank (N ranks)
+  int reducers;     // reducer CTAs per rank (N ranks); 0: the transport's default below
   int unroll;       // MC transport: 16-byte vectors per thread and pipeline stage (4, 8)
   int ctas_per_sm;  // cap of resident CTAs per SM (0: the occupancy)
+  int reducers_mc, reducers_p2p;
 };
-StepTuning g_step = {16384, 32, 4, 4};
+StepTuning g_step = {16384, 0, 4, 4, 96, 192};
 
 template <class K>
 int occupancy(K kernel, size_t smem) {
@@ -368,7 +397,7 @@ int launch_stepn_t(const StepTables& a, StepPeers p, size_t smem, const PackOp& 
   int occ = occupancy(kernel, smem);
   if (g_step.ctas_per_sm > 0 && g_step.ctas_per_sm < occ) occ = g_step.ctas_per_sm;
   const int64_t cap = (int64_t)gp_sm_count_cached() * occ;   // everything resident at once
-  int64_t reducers = g_step.reducers;
+  int64_t reducers = g_step.reducers > 0 ? g_step.reducers : (p.mc_base ? g_step.reducers_mc : g_step.reducers_p2p);
   const int64_t own_tiles = (a.n_tiles + p.n - 1) / p.n;
   if (reducers > own_tiles) reducers = own_tiles;
   if (reducers < 1) reducers = 1;
@@ -531,7 +560,7 @@ int gp_step_adam(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, cons
 int gp_step_set_tuning(const char* key, int value) {
   if (!key) return GP_EINVAL;
   if (!strcmp(key, "tile_elems")) g_step.tile_elems = value < 4096 ? 4096 : value / 4096 * 4096;
-  else if (!strcmp(key, "reducers")) g_step.reducers = value < 1 ? 1 : value;
+  else if (!strcmp(key, "reducers")) g_step.reducers = value < 0 ? 0 : value;
   else if (!strcmp(key, "unroll")) g_step.unroll = value;
   else if (!strcmp(key, "ctas_per_sm")) g_step.ctas_per_sm = value;
   else {

@@ -255,7 +255,9 @@ def main():
                     # Adam divides by sqrt(v) + eps, so elements with |g| ~ eps amplify
                     # the difference (d step / d g ~ alpha / eps): allow the amplified
                     # step error; the mean gradient is judged strictly above
-                    np.testing.assert_allclose(got, q, rtol=tol, atol=2e-4)
+                    # (a 16-bit mean can flip the sign of a gradient within its rounding
+                    # error: such an element moves by up to 2 * alpha per step)
+                    np.testing.assert_allclose(got, q, rtol=tol, atol=2e-4 if adt is None else 8e-3)
             assert actual.t == step
         # every rank holds identical parameters
         flat = torch.cat([p.data.reshape(-1) for _, p in sorted(m.namedparams())])
