@@ -99,6 +99,17 @@ PROTOTYPES = {
     'gp_bn_bwd_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                 c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     'gp_bn_finish_mean_var': (c_int, [c_void_p, c_int, c_int64, c_double, c_void_p, c_void_p]),
+    'gp_bn_fwd_stats_allreduce': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                          c_void_p, c_void_p, c_void_p]),
+    'gp_bn_bwd_stats_allreduce': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,
+                                          c_void_p, c_void_p]),
+    'gp_bn_fwd_apply': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_double, c_double, c_void_p]),
+    'gp_bn_bwd_apply': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
+                                c_void_p, c_void_p]),
     'gp_nccl_load': (c_int, [c_char_p]),
     'gp_nccl_version': (c_int, [_P(c_int)]),
     'gp_nccl_get_unique_id': (c_int, [c_char_p]),
@@ -176,7 +187,8 @@ KERNEL_FUNCS = frozenset([
     'gp_check_finite', 'gp_bn_fwd_stats', 'gp_bn_fwd_mean_var', 'gp_bn_bwd_stats', 'gp_bn_finish_mean_var',
     'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce',
     'gp_unpack_momentum_sgd_hooked', 'gp_unpack_adam_hooked', 'gp_sqnorm', 'gp_scale_by_device',
-    'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family', 'gp_step_momentum_sgd', 'gp_step_adam'])
+    'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family', 'gp_step_momentum_sgd', 'gp_step_adam',
+    'gp_bn_fwd_stats_allreduce', 'gp_bn_bwd_stats_allreduce', 'gp_bn_fwd_apply', 'gp_bn_bwd_apply'])
 
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',

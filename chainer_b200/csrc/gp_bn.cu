@@ -15,9 +15,17 @@
 // a warp-shuffle + shared-memory block reduction, and the last CTA of a channel
 // (atomic ticket) adds the S partials in a fixed order, so the result is
 // deterministic.  Algorithmic bytes: |x| * itemsize read once, 2C * 4 written.
+//
+// N ranks on one NVSwitch box (gp_bn_*_stats_allreduce): the CTA that completes the LAST
+// channel runs the one-shot peer-memory allreduce of the 2C values (gp_p2p_small.cuh) in
+// the same launch -- statistics, allReduce, div_by_size and var = sqmean - mean^2
+// (chainermn/functions/batch_normalization.py:53-68, 79-93) are ONE kernel.
 #include "gp_common.cuh"
 
 namespace {
+
+#include "gp_p2p.cuh"
+#include "gp_p2p_small.cuh"
 
 constexpr int kMaxSplits = 64;
 
@@ -53,7 +61,56 @@ struct BnArgs {
   int out_dtype;
   double out_scale;  // fwd: 1 / (N * HW); bwd: 1
   int finish_var;    // fwd, one rank: write [mean | var] instead of [mean | sqmean]
+  int use_xchg;      // N ranks: the CTA finishing the last channel exchanges `out` (xchg.in)
+  int* done;         // channels completed so far (zero between launches)
+  SmallArgs xchg;
 };
+
+// Channel c's reduction is complete in (t0, t1) of the calling thread (one per CTA):
+// combine the S split partials (the last CTA of the channel does, in fixed order) and
+// write the channel's two outputs.  Returns true when THIS thread wrote them.
+__device__ __forceinline__ bool bn_finish_channel(const BnArgs& a, int64_t c, int sp, double t0,
+                                                  double t1) {
+  if (a.S > 1) {
+    double* part = reinterpret_cast<double*>(a.partials) + ((int64_t)c * a.S) * 2;
+    part[sp * 2 + 0] = t0;
+    part[sp * 2 + 1] = t1;
+    __threadfence();
+    const int ticket = atomicAdd(a.counters + c, 1);
+    if (ticket != a.S - 1) return false;
+    __threadfence();
+    t0 = 0;
+    t1 = 0;
+    for (int k = 0; k < a.S; ++k) {  // fixed order: deterministic
+      t0 += __ldcg(part + k * 2 + 0);
+      t1 += __ldcg(part + k * 2 + 1);
+    }
+    a.counters[c] = 0;  // leave the workspace zeroed for the next call
+  }
+  if (a.finish_var) {
+    // single rank: no allreduce follows, so form var = sqmean - mean^2 here with
+    // the arithmetic of bn_finish_kernel (operands rounded to the output dtype)
+    if (a.out_dtype == GP_F32) {
+      const float m = __double2float_rn(t0 * a.out_scale), q = __double2float_rn(t1 * a.out_scale);
+      reinterpret_cast<float*>(a.out)[c] = m;
+      reinterpret_cast<float*>(a.out)[a.C + c] = __fsub_rn(q, __fmul_rn(m, m));
+    } else if (a.out_dtype == GP_F16) {
+      const float m = __half2float(__double2half(t0 * a.out_scale));
+      const float q = __half2float(__double2half(t1 * a.out_scale));
+      reinterpret_cast<__half*>(a.out)[c] = __float2half_rn(m);
+      reinterpret_cast<__half*>(a.out)[a.C + c] =
+          __float2half_rn(__fsub_rn(q, __half2float(__float2half_rn(__fmul_rn(m, m)))));
+    } else {
+      const double m = t0 * a.out_scale, q = t1 * a.out_scale;
+      reinterpret_cast<double*>(a.out)[c] = m;
+      reinterpret_cast<double*>(a.out)[a.C + c] = __dsub_rn(q, __dmul_rn(m, m));
+    }
+    return true;
+  }
+  store_stat(a.out, a.out_dtype, c, t0 * a.out_scale);
+  store_stat(a.out, a.out_dtype, a.C + c, t1 * a.out_scale);
+  return true;
+}
 
 // MODE 0: a = sum x, b = sum x^2
 // MODE 1: a = sum gy, b = sum gy * xhat           (x holds x_hat)
@@ -170,60 +227,35 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const BnArgs a) {
 
   // block reduction: warp shuffles, then one value per warp through smem
   __shared__ Acc red[2][16];
+  __shared__ int s_exchange;
   s0 = warp_sum(s0);
   s1 = warp_sum(s1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_exchange = 0;
   if (lane == 0) {
     red[0][warp] = s0;
     red[1][warp] = s1;
   }
   __syncthreads();
-  if (warp != 0) return;
-  s0 = lane < nw ? red[0][lane] : (Acc)0;
-  s1 = lane < nw ? red[1][lane] : (Acc)0;
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  if (lane != 0) return;
-
-  double t0 = (double)s0, t1 = (double)s1;
-  if (a.S > 1) {
-    double* part = reinterpret_cast<double*>(a.partials) + ((int64_t)c * a.S) * 2;
-    part[sp * 2 + 0] = t0;
-    part[sp * 2 + 1] = t1;
-    __threadfence();
-    const int ticket = atomicAdd(a.counters + c, 1);
-    if (ticket != a.S - 1) return;
-    __threadfence();
-    t0 = 0;
-    t1 = 0;
-    for (int k = 0; k < a.S; ++k) {  // fixed order: deterministic
-      t0 += __ldcg(part + k * 2 + 0);
-      t1 += __ldcg(part + k * 2 + 1);
+  if (warp == 0) {
+    s0 = lane < nw ? red[0][lane] : (Acc)0;
+    s1 = lane < nw ? red[1][lane] : (Acc)0;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0 && bn_finish_channel(a, c, sp, (double)s0, (double)s1) && a.use_xchg) {
+      // N ranks: whoever completes the last channel exchanges the 2C values
+      __threadfence();
+      if (atomicAdd(a.done, 1) == (int)a.C - 1) {
+        *a.done = 0;
+        s_exchange = 1;
+      }
     }
-    a.counters[c] = 0;  // leave the workspace zeroed for the next call
   }
-  if (a.finish_var) {
-    // single rank: no allreduce follows, so form var = sqmean - mean^2 here with
-    // the arithmetic of bn_finish_kernel (operands rounded to the output dtype)
-    if (a.out_dtype == GP_F32) {
-      const float m = __double2float_rn(t0 * a.out_scale), q = __double2float_rn(t1 * a.out_scale);
-      reinterpret_cast<float*>(a.out)[c] = m;
-      reinterpret_cast<float*>(a.out)[a.C + c] = __fsub_rn(q, __fmul_rn(m, m));
-    } else if (a.out_dtype == GP_F16) {
-      const float m = __half2float(__double2half(t0 * a.out_scale));
-      const float q = __half2float(__double2half(t1 * a.out_scale));
-      reinterpret_cast<__half*>(a.out)[c] = __float2half_rn(m);
-      reinterpret_cast<__half*>(a.out)[a.C + c] =
-          __float2half_rn(__fsub_rn(q, __half2float(__float2half_rn(__fmul_rn(m, m)))));
-    } else {
-      const double m = t0 * a.out_scale, q = t1 * a.out_scale;
-      reinterpret_cast<double*>(a.out)[c] = m;
-      reinterpret_cast<double*>(a.out)[a.C + c] = __dsub_rn(q, __dmul_rn(m, m));
-    }
-    return;
-  }
-  store_stat(a.out, a.out_dtype, c, t0 * a.out_scale);
-  store_stat(a.out, a.out_dtype, a.C + c, t1 * a.out_scale);
+  if (!a.use_xchg) return;
+  __syncthreads();
+  if (!s_exchange) return;
+  __threadfence();            // the other CTAs' channel outputs (read through L2 below)
+  small_exchange(a.xchg);
 }
 
 // buf[0:2C] *= scale (rounded to T); var[c] = sqmean[c] - mean[c]^2
@@ -272,9 +304,13 @@ int launch_x(int x_dtype, int gy_dtype, const BnArgs& a, bool vec, dim3 grid, in
   }
 }
 
+size_t ws_counters_bytes(int64_t C) { return (size_t)(((C * 4 + 255) / 256) * 256); }
+size_t ws_partials_bytes(int64_t C) { return (size_t)(C * kMaxSplits * 2 * sizeof(double)); }
+
 int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype, const void* mean,
               const void* inv_std, int stat_dtype, int64_t N, int64_t C, int64_t HW, void* out,
-              int out_dtype, void* workspace, double out_scale, void* stream, int finish_var = 0) {
+              int out_dtype, void* workspace, double out_scale, void* stream, int finish_var = 0,
+              P2PComm* comm = nullptr) {
   if (N <= 0 || C <= 0 || HW <= 0) return 0;
   if (out_dtype != GP_F16 && out_dtype != GP_F32 && out_dtype != GP_F64) {
     gp_set_error("gp_bn_stats: unsupported output dtype id %d", out_dtype);
@@ -289,6 +325,26 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
   a.N = N; a.C = C; a.HW = HW;
   a.out = out; a.out_dtype = out_dtype; a.out_scale = out_scale;
   a.finish_var = finish_var;
+  a.use_xchg = 0;
+  a.done = nullptr;
+  if (comm) {
+    // local statistics go to a staging area of the workspace; the exchange writes `out`
+    if (!workspace || out_dtype != GP_F32 || 2 * C > comm->small_cap || comm->small_cap <= 0) {
+      gp_set_error("gp_bn_*_stats_allreduce: needs a workspace, float32 statistics and 2C <= %lld",
+                   (long long)comm->small_cap);
+      return GP_EINVAL;
+    }
+    char* ws = reinterpret_cast<char*>(workspace) + ws_counters_bytes(C) + ws_partials_bytes(C);
+    a.done = reinterpret_cast<int*>(ws);
+    float* local = reinterpret_cast<float*>(ws + 256);
+    a.out = local;
+    a.use_xchg = 1;
+    small_args_from(comm, &a.xchg, 1.0 / comm->n);
+    a.xchg.in = local;
+    a.xchg.out = reinterpret_cast<float*>(out);
+    a.xchg.n_elems = (int)(2 * C);
+    a.xchg.C = mode == 0 ? (int)C : 0;
+  }
 
   // splits over the batch axis: enough CTAs for ~16 per SM (several waves, so that
   // the uneven last wave is short) while keeping >= ~8 KB of rows per CTA.
@@ -305,7 +361,7 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
   a.rows_per_split = (int)((N + S - 1) / S);
   a.S = (int)((N + a.rows_per_split - 1) / a.rows_per_split);
   a.counters = reinterpret_cast<int*>(workspace);
-  a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((C * 4 + 255) / 256) * 256);
+  a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_counters_bytes(C));
 
   const int xs = gp_itemsize(x_dtype), gs = gp_itemsize(gy_dtype);
   bool vec = (HW % 4 == 0) && ((uintptr_t)x % (xs == 2 ? 8 : 16) == 0);
@@ -328,9 +384,35 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
 
 }  // namespace
 
+// [channel tickets | split partials | "channels done" counter | local 2C statistics]
 extern "C" size_t gp_bn_workspace_bytes(int64_t C) {
   if (C < 0) C = 0;
-  return (size_t)(((C * 4 + 255) / 256) * 256 + C * kMaxSplits * 2 * sizeof(double));
+  return ws_counters_bytes(C) + ws_partials_bytes(C) + 256 + (size_t)(2 * C * sizeof(float) + 255) / 256 * 256;
+}
+
+extern "C" int gp_bn_fwd_stats_allreduce(void* p2p_comm, const void* x, int x_dtype, int64_t N,
+                                         int64_t C, int64_t HW, void* out_mean_var,
+                                         void* workspace, void* stream) {
+  if (!p2p_comm) {
+    gp_set_error("gp_bn_fwd_stats_allreduce: no peer-memory communicator");
+    return GP_EINVAL;
+  }
+  const double inv = (N > 0 && HW > 0) ? 1.0 / ((double)N * (double)HW) : 0.0;
+  return bn_launch(0, x, x_dtype, nullptr, x_dtype, nullptr, nullptr, GP_F32, N, C, HW,
+                   out_mean_var, GP_F32, workspace, inv, stream, 0, (P2PComm*)p2p_comm);
+}
+
+extern "C" int gp_bn_bwd_stats_allreduce(void* p2p_comm, const void* gy, int gy_dtype,
+                                         const void* xhat_or_x, int x_dtype, const void* mean,
+                                         const void* inv_std, int stat_dtype, int64_t N, int64_t C,
+                                         int64_t HW, void* out, void* workspace, void* stream) {
+  if (!p2p_comm) {
+    gp_set_error("gp_bn_bwd_stats_allreduce: no peer-memory communicator");
+    return GP_EINVAL;
+  }
+  const int mode = (mean != nullptr && inv_std != nullptr) ? 2 : 1;
+  return bn_launch(mode, xhat_or_x, x_dtype, gy, gy_dtype, mean, inv_std, stat_dtype, N, C, HW,
+                   out, GP_F32, workspace, 1.0, stream, 0, (P2PComm*)p2p_comm);
 }
 
 extern "C" int gp_bn_fwd_stats(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW,

@@ -168,55 +168,9 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
 // 1/size scale and (forward statistics) forms var = sqmean - mean^2 -- the work of
 // allReduce + div_by_size + the var kernel in ONE single-CTA launch whose latency
 // is one NVLink store round.  Receive areas are double-buffered by call parity.
-struct SmallArgs {
-  float* recv[kMaxRanks];
-  uint32_t* flags[kMaxRanks];
-  int rank, n;
-  int64_t cap;
-  uint32_t epoch;
-  unsigned long long timeout_ns;
-  const float* in;
-  float* out;
-  int n_elems;
-  int C;         // > 0: out[C + c] = out[C + c] - out[c]^2 after scaling (mean | var)
-  float scale_f;
-  double scale_d;
-  int scale_mode;
-};
+#include "gp_p2p_small.cuh"
 
-__global__ void __launch_bounds__(1024) p2p_small_kernel(const SmallArgs a) {
-  const int par = a.epoch & 1;
-  // 1. my contribution into slot [rank] of every rank (own included)
-  for (int i = threadIdx.x; i < a.n_elems; i += blockDim.x) {
-    const float v = a.in[i];
-    for (int k = 0; k < a.n; ++k)
-      a.recv[k][((int64_t)par * a.n + a.rank) * a.cap + i] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < a.n) {
-    __threadfence_system();
-    st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
-    spin_until(a.flags[a.rank] + threadIdx.x, a.epoch, a.timeout_ns);
-  }
-  __syncthreads();
-  // 2. rank-order sum of the N slots, scale (x * (1.0/N) in double or exactly in
-  //    float for 2^-k, one rounding), optional variance
-  const float* mine = a.recv[a.rank] + (int64_t)par * a.n * a.cap;
-  for (int i = threadIdx.x; i < a.n_elems; i += blockDim.x) {
-    float acc = __ldcg(mine + i);
-    for (int k = 1; k < a.n; ++k) acc = __fadd_rn(acc, __ldcg(mine + (int64_t)k * a.cap + i));
-    if (a.scale_mode == 1) acc = __fmul_rn(acc, a.scale_f);
-    else if (a.scale_mode == 2) acc = __double2float_rn(__dmul_rn((double)acc, a.scale_d));
-    a.out[i] = acc;
-  }
-  if (a.C > 0) {
-    __syncthreads();
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      const float m = a.out[c];
-      a.out[a.C + c] = __fsub_rn(a.out[a.C + c], __fmul_rn(m, m));
-    }
-  }
-}
+__global__ void __launch_bounds__(1024) p2p_small_kernel(const SmallArgs a) { small_exchange(a); }
 
 int g_p2p_ctas = 0;     // 0: default
 int g_p2p_threads = 512;
@@ -385,23 +339,11 @@ int gp_p2p_allreduce_small(void* comm, const void* in, void* out, int64_t n_elem
     return GP_EINVAL;
   }
   SmallArgs a;
-  for (int k = 0; k < c->n; ++k) {
-    a.recv[k] = c->small_recv[k];
-    a.flags[k] = c->small_flags[k];
-  }
-  a.rank = c->rank;
-  a.n = c->n;
-  a.cap = c->small_cap;
-  a.epoch = ++c->small_epoch;
-  a.timeout_ns = g_gp_peer_timeout_ns;
+  small_args_from(c, &a, scale);
   a.in = (const float*)in;
   a.out = (float*)out;
   a.n_elems = (int)n_elems;
   a.C = (int)C;
-  const ScaleArg s = make_scale(scale);
-  a.scale_f = s.fs;
-  a.scale_d = s.ds;
-  a.scale_mode = s.mode;
   int threads = 1024;
   while (threads > 64 && threads / 2 >= n_elems) threads >>= 1;
   p2p_small_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(a);

@@ -19,20 +19,22 @@
 //
 // N ranks (2, 4, 8 on one NVSwitch box): tile t is OWNED by rank t % N.
 //   worker CTAs   pack their tiles in tile order; after each tile one
-//                 `red.release.sys.add` on the owner's counter cnt[t];
+//                 `st.release.sys` of the epoch into the owner's word packed[t][rank];
 //                 then, per tile, wait for the owner's flag[t] and run the fused
 //                 update on it;
 //   reducer CTAs  (the first `reducers` CTAs) take the rank's own tiles in order:
-//                 wait until cnt[t] shows all N ranks have packed it, sum the N
+//                 wait until packed[t][0..N-1] show that all N ranks have packed it, sum the N
 //                 copies -- `multimem.ld_reduce` + `multimem.st` through the NVSwitch
 //                 (transport MC) or N peer loads added in rank order + N peer stores
 //                 (transport P2P, bit-exact with the oracle) -- then publish
 //                 flag[t] = epoch to every rank.
 // The NVLink-bound reduction of tile t therefore overlaps the HBM-bound pack of later
 // tiles and update of earlier ones inside ONE launch, with no kernel-level barrier
-// (the allreduce kernels need two) and no chunk launches.  Counters and flags are
-// monotonic (cnt[t] == N * epoch, flag[t] == epoch after step `epoch`), live in a
-// per-rank block shared through CUDA IPC, and every wait polls LOCAL memory.
+// (the allreduce kernels need two) and no chunk launches.  Every word carries the EPOCH
+// of the step that wrote it (packed[t][r] == flag[t] == epoch once tile t is through), so a
+// wait never depends on the history of a tile: the element count may change from step to
+// step.  The words live in a per-rank block shared through CUDA IPC, and every wait polls
+// LOCAL memory.
 // Every CTA of the launch is resident at once (the grid is capped by the occupancy),
 // which the cross-rank waits require.
 #include <string.h>
@@ -110,7 +112,7 @@ struct PackUpd {
 
 // ------------------------------------------------------------------- N ranks --
 struct StepPeers {
-  uint32_t* words[kMaxRanks];  // every rank's [cnt: tile_cap | flag: tile_cap]
+  uint32_t* words[kMaxRanks];  // every rank's [packed: tile_cap x kMaxRanks | flag: tile_cap]
   void* bufs[kMaxRanks];       // P2P: this process's mappings of the packed buffers
   char* mc_base;               // MC: multicast address of the packed buffer
   int64_t tile_cap;
@@ -289,11 +291,11 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
   extern __shared__ int64_t s_csum[];
   if ((int)blockIdx.x < p.reducers) {
     // ------------------------------------------------------------- reducer ----
-    const uint32_t* cnt = p.words[p.rank];
-    const uint32_t all_packed = p.epoch * (uint32_t)p.n;
+    const uint32_t* packed = p.words[p.rank];
     constexpr int E = 16 / (int)sizeof(B);
     for (int64_t t = p.rank + (int64_t)blockIdx.x * p.n; t < a.n_tiles; t += (int64_t)p.reducers * p.n) {
-      if (threadIdx.x == 0) spin_until(cnt + t, all_packed, p.timeout_ns);
+      // thread r waits for rank r's "tile t packed" word
+      if ((int)threadIdx.x < p.n) spin_until(packed + t * kMaxRanks + threadIdx.x, p.epoch, p.timeout_ns);
       __syncthreads();
       const int64_t lo = t * a.tile_elems;
       const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
@@ -302,7 +304,8 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
       Red::run(p, lo / E, (hi + E - 1) / E);
       __syncthreads();
       // release: cumulative over the CTA's stores (ordered before it by bar.sync)
-      if ((int)threadIdx.x < p.n) st_release_sys(p.words[threadIdx.x] + p.tile_cap + t, p.epoch);
+      if ((int)threadIdx.x < p.n)
+        st_release_sys(p.words[threadIdx.x] + p.tile_cap * kMaxRanks + t, p.epoch);
     }
     return;
   }
@@ -315,9 +318,10 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
     const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
     gpw::walk_range<PackOp, B, 4, 0, GP_F32>(cs, a.segs, a.n_segs, lo, hi, pk);
     __syncthreads();
-    if (threadIdx.x == 0) red_add_release_sys(p.words[t % p.n] + t, 1u);
+    // release: cumulative over the CTA's stores (ordered before it by bar.sync)
+    if (threadIdx.x == 0) st_release_sys(p.words[t % p.n] + t * kMaxRanks + p.rank, p.epoch);
   }
-  const uint32_t* flag = p.words[p.rank] + p.tile_cap;
+  const uint32_t* flag = p.words[p.rank] + p.tile_cap * kMaxRanks;
   for (int64_t t = w; t < a.n_tiles; t += nw) {
     // the acquire also drops this SM's L1 lines of the tile (written by pack earlier)
     if (threadIdx.x == 0) spin_until(flag + t, p.epoch, p.timeout_ns);
@@ -506,7 +510,9 @@ int gp_step_supported(int n_ranks, int buf_dtype, int layout_hint, double scale,
   return step_covers(n_ranks, buf_dtype, layout_hint, scale) ? 1 : 0;
 }
 
-size_t gp_step_words_bytes(int64_t tile_cap) { return (size_t)tile_cap * 2 * sizeof(uint32_t); }
+size_t gp_step_words_bytes(int64_t tile_cap) {
+  return (size_t)tile_cap * (kMaxRanks + 1) * sizeof(uint32_t);
+}
 
 int gp_step_tile_elems(void) { return g_step.tile_elems; }
 

@@ -118,15 +118,16 @@ class _NcclImpl(object):
                                    HW, _dev.device_ptr(buf), _dev.dtype_id(gdt),
                                    _workspace(self.comm, C), 0)
             return _halves(buf, C)
-        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
-                            _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
         p2p = _small_p2p(self.comm, gdt, 2 * C)
         if p2p is not None:
-            # allReduce + div_by_size + var in ONE kernel over NVLink peer memory
-            out = _new_like(gamma, 2 * C, gdt)
-            p2p.allreduce_small(_dev.device_ptr(buf), _dev.device_ptr(out), 2 * C, C,
-                                1.0 / self.comm.size, None)
-            return _halves(out, C)
+            # statistics + allReduce + div_by_size + var in ONE kernel: the CTA that finishes
+            # the last channel exchanges the 2C values over NVLink peer memory
+            lib.gp_bn_fwd_stats_allreduce(p2p.handle, _dev.device_ptr(x),
+                                          _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                                          _dev.device_ptr(buf), _workspace(self.comm, C), 0)
+            return _halves(buf, C)
+        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                            _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
         _allreduce_in_place(self.comm, buf, 2 * C, gdt)
         mean, var = _halves(buf, C)
         # buf *= 1/size; var = sqmean - mean**2 (written over sqmean)
@@ -169,6 +170,17 @@ class _NcclImpl(object):
         N, HW = _check_layout(axis, gy, C)
         gdt = _dev.array_dtype(gamma)
         buf = _new_like(gamma, 2 * C, gdt)
+        p2p = _small_p2p(self.comm, gdt, 2 * C) if self.comm.size > 1 else None
+        if p2p is not None:
+            # statistics + allReduce + div_by_size in ONE kernel (see get_mean_and_var)
+            lib.gp_bn_bwd_stats_allreduce(p2p.handle, _dev.device_ptr(gy),
+                                          _dev.dtype_id(_dev.array_dtype(gy)), _dev.device_ptr(x),
+                                          _dev.dtype_id(_dev.array_dtype(x)), _dev.device_ptr(mean),
+                                          _dev.device_ptr(inv_std),
+                                          _dev.dtype_id(_dev.array_dtype(mean)), N, C, HW,
+                                          _dev.device_ptr(buf), _workspace(self.comm, C), 0)
+            gbeta, ggamma = _halves(buf, C)
+            return gbeta, ggamma
         lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.dtype_id(_dev.array_dtype(gy)),
                             _dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)),
                             _dev.device_ptr(mean), _dev.device_ptr(inv_std),
@@ -270,6 +282,46 @@ class MultiNodeBNImplSelector:
             return _NcclImpl(self.comm)
         else:
             return _MpiImpl(self.comm)
+
+
+def fwd_apply(x, mean, var, gamma, beta, eps, running_mean=None, running_var=None, decay=0.9,
+              adjust=1.0):
+    """Everything of the BN forward that follows the statistics, ONE launch
+    (``chainer/functions/normalization/batch_normalization.py:40-77``): ``inv_std =
+    rsqrt(var + eps)``, ``y = gamma * (x - mean) * inv_std + beta`` and, when given, the
+    in-place update of the running statistics.  Returns ``(y, inv_std)``."""
+    lib = _lib.get()
+    C = _dev.array_size(gamma)
+    N, HW = _check_layout(None, x, C)
+    sdt = _dev.array_dtype(gamma)
+    y = _dev.empty_like(x)
+    inv_std = _new_like(gamma, C, sdt)
+    rdt = _dev.array_dtype(running_mean) if running_mean is not None else sdt
+    lib.gp_bn_fwd_apply(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                        _dev.device_ptr(mean), _dev.device_ptr(var), _dev.device_ptr(gamma),
+                        _dev.device_ptr(beta), _dev.dtype_id(sdt), float(eps), _dev.device_ptr(y),
+                        _dev.device_ptr(inv_std),
+                        _dev.device_ptr(running_mean) if running_mean is not None else None,
+                        _dev.device_ptr(running_var) if running_var is not None else None,
+                        _dev.dtype_id(rdt), float(decay), float(adjust), 0)
+    return y, inv_std
+
+
+def bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta):
+    """``gx`` of the BN backward, ONE launch with ``x_hat`` formed on the fly
+    (``chainer/functions/normalization/batch_normalization.py:105-133``)."""
+    lib = _lib.get()
+    C = _dev.array_size(gamma)
+    N, HW = _check_layout(None, x, C)
+    sdt = _dev.array_dtype(gamma)
+    gx = _dev.empty_like(x)
+    inv_m = float(np.dtype(sdt).type(1.0 / (N * HW))) if not isinstance(sdt, str) else 1.0 / (N * HW)
+    lib.gp_bn_bwd_apply(_dev.device_ptr(gy), _dev.dtype_id(_dev.array_dtype(gy)),
+                        _dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                        _dev.device_ptr(mean), _dev.device_ptr(inv_std), _dev.device_ptr(gamma),
+                        _dev.device_ptr(ggamma), _dev.device_ptr(gbeta), _dev.dtype_id(sdt),
+                        inv_m, _dev.device_ptr(gx), 0)
+    return gx
 
 
 def mean_and_var(comm, x, gamma):

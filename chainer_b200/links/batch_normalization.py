@@ -4,13 +4,13 @@
 Constructor arguments, parameters (``gamma``, ``beta``), persistents
 (``avg_mean``, ``avg_var`` -- initialised to ZEROS like the reference, ``:57-60``
 --, ``N``), ``decay`` / ``eps`` / ``finetune`` semantics and backend validation
-follow the reference.  Only the STATISTICS are computed by this package's
-kernels (``functions/batch_normalization._NcclImpl``); the elementwise
-normalisation ``y = gamma * (x - mean) * inv_std + beta`` and ``gx`` stay on the
-framework's own path -- Chainer + CuPy in the reference
-(``chainer/functions/normalization/batch_normalization.py:46-47, 121-133``),
-``torch`` ops with ``torch.autograd`` here, since that is the array library of
-this image.
+follow the reference.  The statistics (+ their exchange over the workers) and the
+elementwise halves -- ``y = gamma * (x - mean) * inv_std + beta`` with ``inv_std`` and
+the running-statistics update, and ``gx`` with ``x_hat`` formed on the fly
+(``chainer/functions/normalization/batch_normalization.py:40-77, 105-133``) -- are
+this package's kernels (``functions/batch_normalization``): 2 launches forward and 2
+backward per layer; ``torch.autograd`` only carries the graph, since torch is the array
+library of this image.
 """
 import numpy as np
 
@@ -38,14 +38,17 @@ class _MNBNFunction(object):
 
         class MNBN(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, x, gamma, beta, impl, eps):
+            def forward(ctx, x, gamma, beta, impl, eps, running_mean, running_var, decay):
                 axis = (0,) + tuple(range(2, x.dim()))
                 x = x.contiguous()
                 mean, var = impl.get_mean_and_var(axis, gamma, x)
-                inv_std = torch.rsqrt(var + eps)
-                shape = (1, -1) + (1,) * (x.dim() - 2)
-                y = (gamma.view(shape) * (x - mean.view(shape).to(x.dtype)) *
-                     inv_std.view(shape).to(x.dtype) + beta.view(shape)).to(x.dtype)
+                # y, inv_std and the running statistics in ONE launch (gp_bn_fwd_apply); m is
+                # the LOCAL element count per channel (chainer/functions/normalization/
+                # batch_normalization.py:50-52)
+                m = x.numel() // gamma.numel()
+                adjust = m / max(m - 1., 1.)
+                y, inv_std = mnbn_functions.fwd_apply(x, mean, var, gamma, beta, eps,
+                                                      running_mean, running_var, decay, adjust)
                 ctx.impl = impl
                 ctx.save_for_backward(x, gamma, mean, inv_std)
                 ctx.mark_non_differentiable(mean, var)
@@ -58,12 +61,9 @@ class _MNBNFunction(object):
                 gy = gy.contiguous()
                 gbeta, ggamma = ctx.impl.get_ggamma_and_gbeta_from_x(axis, gamma, gy, x, mean,
                                                                      inv_std)
-                shape = (1, -1) + (1,) * (x.dim() - 2)
-                inv_m = 1.0 / (x.numel() // gamma.numel())
-                x_hat = (x - mean.view(shape)) * inv_std.view(shape)
-                gx = (gamma * inv_std).view(shape) * (
-                    gy - (x_hat * ggamma.view(shape) + gbeta.view(shape)) * inv_m)
-                return gx.to(x.dtype), ggamma, gbeta, None, None
+                # gx in ONE launch, x_hat formed on the fly (gp_bn_bwd_apply)
+                gx = mnbn_functions.bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta)
+                return gx, ggamma, gbeta, None, None, None, None, None
 
         cls._fn = MNBN
         return MNBN
@@ -135,19 +135,14 @@ class MultiNodeBatchNormalization(link.Link):
                 decay = 1. - 1. / self.N
             else:
                 decay = self.decay
-            y, mean, var = _MNBNFunction.get().apply(x, gamma, beta, self._impl(), self.eps)
-            # running statistics (chainer/functions/normalization/
-            # batch_normalization.py:50-77): m is the LOCAL element count per channel
-            m = x.numel() // size
-            adjust = m / max(m - 1., 1.)
-            with torch.no_grad():
-                self.avg_mean.mul_(decay).add_(mean.to(self._tdt), alpha=1 - decay)
-                self.avg_var.mul_(decay).add_(var.to(self._tdt), alpha=(1 - decay) * adjust)
+            y, mean, var = _MNBNFunction.get().apply(x, gamma, beta, self._impl(), self.eps,
+                                                     self.avg_mean, self.avg_var, decay)
             return y
-        shape = (1, -1) + (1,) * (x.dim() - 2)
-        inv_std = torch.rsqrt(self.avg_var + self.eps)
-        return (gamma.view(shape) * (x - self.avg_mean.view(shape)) * inv_std.view(shape) +
-                beta.view(shape)).to(x.dtype)
+        # fixed statistics (evaluation): the same elementwise kernel, one launch
+        with torch.no_grad():
+            y, _ = mnbn_functions.fwd_apply(x.contiguous(), self.avg_mean, self.avg_var, gamma,
+                                            beta, self.eps)
+        return y
 
     def start_finetuning(self):
         self.N = 0

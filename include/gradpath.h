@@ -236,6 +236,38 @@ int gp_bn_bwd_stats(const void* gy, int gy_dtype, const void* xhat_or_x, int x_d
  * scale: buf[k] *= scale first.  out_var[C] may alias buf + C. */
 int gp_bn_finish_mean_var(void* buf, int dtype, int64_t C, double scale, void* out_var,
                           void* stream);
+/* Statistics + exchange in ONE kernel for N ranks on one NVSwitch box: the CTA that
+ * completes the last channel runs the one-shot peer-memory allreduce of the 2C float32
+ * values (allReduce + div_by_size [+ var = sqmean - mean^2]) inside the same launch.
+ * Replaces the whole of _NcclImpl.get_mean_and_var / get_ggamma_and_gbeta
+ * (chainermn/functions/batch_normalization.py:44-68, 70-93).  `p2p_comm`: a gp_p2p_create
+ * handle whose small-message areas are set (gp_p2p_set_small), 2C <= their capacity;
+ * `out`: float32 [2C] = [mean | var] over all ranks (forward) / the mean over ranks of
+ * [sum gy | sum gy * x_hat] (backward).  Collective: every rank launches it. */
+int gp_bn_fwd_stats_allreduce(void* p2p_comm, const void* x, int x_dtype, int64_t N, int64_t C,
+                              int64_t HW, void* out_mean_var, void* workspace, void* stream);
+int gp_bn_bwd_stats_allreduce(void* p2p_comm, const void* gy, int gy_dtype, const void* xhat_or_x,
+                              int x_dtype, const void* mean, const void* inv_std, int stat_dtype,
+                              int64_t N, int64_t C, int64_t HW, void* out, void* workspace,
+                              void* stream);
+/* The elementwise halves of batch normalisation (csrc/gp_bn_apply.cu), one launch each.
+ * Forward (chainer/functions/normalization/batch_normalization.py:40-77, 864-867):
+ *   inv_std = rsqrt(var + eps);  y = gamma * (x - mean) * inv_std + beta;
+ *   r_mean = r_mean * decay + mean * (1 - decay);
+ *   r_var  = r_var  * decay + var  * (1 - decay) * adjust        (running_* may be NULL)
+ * replacing the rsqrt, `bn_fwd` and `update_mean_var` launches; inv_std_out [C] may be NULL.
+ * Backward (:105-133): gx = (gamma * inv_std) * (gy - (x_hat * ggamma + gbeta) * inv_m)
+ * with x_hat = (x - mean) * inv_std formed on the fly (the reference materialises it).
+ * x, y, gy, gx: [N, C, HW] contiguous, one dtype; statistics / gamma / beta: [C] of
+ * stat_dtype. */
+int gp_bn_fwd_apply(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW, const void* mean,
+                    const void* var, const void* gamma, const void* beta, int stat_dtype,
+                    double eps, void* y, void* inv_std_out, void* running_mean, void* running_var,
+                    int running_dtype, double decay, double adjust, void* stream);
+int gp_bn_bwd_apply(const void* gy, int gy_dtype, const void* x, int x_dtype, int64_t N, int64_t C,
+                    int64_t HW, const void* mean, const void* inv_std, const void* gamma,
+                    const void* ggamma, const void* gbeta, int stat_dtype, double inv_m, void* gx,
+                    void* stream);
 
 /* ------------------------------------------------------------------ NCCL -- */
 /* Thin wrappers over libnccl.so.2, resolved with dlopen at gp_nccl_load time;
@@ -436,9 +468,11 @@ int gp_step_adam(void* p2p_comm, void* mc_ptr, void* buffer, int buf_dtype, cons
                  double one_minus_beta1, double one_minus_beta2, double eps, double eta,
                  double weight_decay_rate, double lower, double upper, int adam_flags,
                  int write_grad, int layout_hint, void* stream);
-/* per-tile words of the N-rank step: [tile_cap "packed" counters | tile_cap "reduced"
- * flags] (uint32) per rank, zeroed, shared through gp_ipc_*; tile_elems (a multiple of
- * 4096, gp_step_tile_elems() is the tuned default) is fixed for the life of the words */
+/* per-tile words of the N-rank step: [tile_cap x 8 "packed by rank r" words | tile_cap
+ * "reduced" flags] (uint32, each holding the epoch of the step that wrote it) per rank,
+ * zeroed, shared through gp_ipc_*; tile_elems (a multiple of 4096, gp_step_tile_elems()
+ * is the tuned default) is fixed for the life of the words; the element count may
+ * change from step to step */
 size_t gp_step_words_bytes(int64_t tile_cap);
 int gp_step_tile_elems(void);
 int gp_p2p_set_step_words(void* p2p_comm, void* const* blocks, int64_t tile_cap, int64_t tile_elems);

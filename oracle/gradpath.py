@@ -373,3 +373,58 @@ def x_hat(x, mean, inv_std):
     x_mu = x - mean.reshape(shape)
     x_mu *= inv_std.reshape(shape)
     return x_mu
+
+
+# --------------------------------------- batch-norm elementwise halves ------
+def _interm(x_dtype, stat_dtype):
+    """The type the reference's `bn_fwd` / `bn_bwd` ElementwiseKernels compute in: float16
+    operands are promoted to float, so float unless a float64 is involved."""
+    return np.float64 if np.float64 in (np.dtype(x_dtype), np.dtype(stat_dtype)) else np.float32
+
+
+def bn_inv_std(var, eps):
+    """`inv_std = rsqrt(var + eps)` (chainer/functions/normalization/
+    batch_normalization.py:40-45), correctly rounded in the statistics' type."""
+    T = np.float64 if var.dtype == np.float64 else np.float32
+    v = var.astype(T) + T(eps)
+    return (1.0 / np.sqrt(v.astype(np.float64))).astype(T).astype(var.dtype)
+
+
+def bn_fwd_apply(x, mean, var, gamma, beta, eps):
+    """The `bn_fwd` kernel (:864-867) `y = gamma * (x - mean) * inv_std + beta` with
+    `inv_std = rsqrt(var + eps)`, every operation rounded to the intermediate type in the
+    kernel's order (no FMA contraction), result cast to x.dtype."""
+    T = _interm(x.dtype, gamma.dtype)
+    shape = (1, -1) + (1,) * (x.ndim - 2)
+    inv_std = bn_inv_std(var, eps).astype(T).reshape(shape)
+    g, b, m = (a.astype(T).reshape(shape) for a in (gamma, beta, mean))
+    y = g * (x.astype(T) - m)
+    y = y * inv_std
+    y = y + b
+    return y.astype(x.dtype)
+
+
+def bn_running_update(running_mean, running_var, mean, var, decay, adjust):
+    """`update_mean_var` (:69-77), in place:
+    r_mean = r_mean * decay + mean * (1 - decay); r_var = r_var * decay + var * (1 - decay) * adjust."""
+    T = _interm(mean.dtype, running_mean.dtype)
+    d, a = T(decay), T(adjust)
+    omd = T(1) - d
+    rm = running_mean.astype(T) * d + mean.astype(T) * omd
+    rv = running_var.astype(T) * d + (var.astype(T) * omd) * a
+    running_mean[...] = rm.astype(running_mean.dtype)
+    running_var[...] = rv.astype(running_var.dtype)
+
+
+def bn_bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta, inv_m):
+    """The `bn_bwd` kernel (:121-133) with x_hat formed on the fly (`_x_hat`, :826-829):
+    gx = (gamma * inv_std) * (gy - (x_hat * ggamma + gbeta) * inv_m)."""
+    T = _interm(x.dtype, gamma.dtype)
+    shape = (1, -1) + (1,) * (x.ndim - 2)
+    m, s, g, gg, gb = (a.astype(T).reshape(shape) for a in (mean, inv_std, gamma, ggamma, gbeta))
+    xh = (x.astype(T) - m) * s
+    t = xh * gg
+    t = t + gb
+    t = t * T(inv_m)
+    gx = (g * s) * (gy.astype(T) - t)
+    return gx.astype(x.dtype)

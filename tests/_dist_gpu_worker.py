@@ -185,11 +185,15 @@ def main():
     from chainer_b200 import _lib as _l
     _l.get().gp_step_set_tuning(b'tile_elems', 4096)
     step_launches = 0
-    for opt_name, adt, tol, use_step in (
-            ('momentum_sgd', None, 1e-6, False), ('adam', None, 1e-6, False),
-            ('momentum_sgd', np.float16, 2e-3, False),
-            ('momentum_sgd', None, 1e-6, True), ('adam', None, 1e-6, True),
-            ('momentum_sgd', np.float16, 2e-3, True), ('adam', 'bfloat16', 1.6e-2, True)):
+    # (the element count changes between the configurations -- fewer tiles, more tiles, a
+    # larger buffer: the step's per-tile words must not depend on history)
+    for opt_name, adt, tol, use_step, n_target in (
+            ('momentum_sgd', None, 1e-6, False, 600000), ('adam', None, 1e-6, False, 600000),
+            ('momentum_sgd', np.float16, 2e-3, False, 600000),
+            ('momentum_sgd', None, 1e-6, True, 600000), ('adam', None, 1e-6, True, 20000),
+            ('momentum_sgd', np.float16, 2e-3, True, 900000),
+            ('adam', 'bfloat16', 1.6e-2, True, 150000)):
+        wl = workloads.scaled_histogram(n_target)
         comm.use_step = use_step
         comm.set_config('allreduce_grad_dtype', adt)
         comm.bucket_bytes = 256 << 10                 # several buckets

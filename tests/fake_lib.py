@@ -263,7 +263,7 @@ class FakeLib(object):
         return 16384
 
     def gp_step_words_bytes(self, cap):
-        return cap * 8
+        return cap * 36
 
     def gp_step_set_tuning(self, key, value):
         self.tuning['step_' + (key.decode() if isinstance(key, bytes) else key)] = value
@@ -453,6 +453,33 @@ class FakeLib(object):
         var = s[C:] - np.square(s[:C])
         _view(buf, 2 * C, dt)[...] = s
         _view(out_var, C, dt)[...] = var
+        return 0
+
+    def gp_bn_fwd_apply(self, x, x_dtype, N, C, HW, mean, var, gamma, beta, stat_dtype, eps, y,
+                        inv_std_out, running_mean, running_var, running_dtype, decay, adjust, stream):
+        self.calls.append(('gp_bn_fwd_apply', (N, C, HW)))
+        xdt, sdt = _ID2DT[x_dtype], _ID2DT[stat_dtype]
+        xs = _view(x, N * C * HW, xdt).reshape(N, C, HW)
+        m, v = _view(mean, C, sdt), _view(var, C, sdt)
+        _view(y, N * C * HW, xdt).reshape(N, C, HW)[...] = og.bn_fwd_apply(
+            xs, m, v, _view(gamma, C, sdt), _view(beta, C, sdt), eps)
+        if inv_std_out:
+            _view(inv_std_out, C, sdt)[...] = og.bn_inv_std(np.array(v), eps)
+        if running_mean:
+            rdt = _ID2DT[running_dtype]
+            og.bn_running_update(_view(running_mean, C, rdt), _view(running_var, C, rdt),
+                                 np.array(m), np.array(v), decay, adjust)
+        return 0
+
+    def gp_bn_bwd_apply(self, gy, gy_dtype, x, x_dtype, N, C, HW, mean, inv_std, gamma, ggamma, gbeta,
+                        stat_dtype, inv_m, gx, stream):
+        self.calls.append(('gp_bn_bwd_apply', (N, C, HW)))
+        xdt, sdt = _ID2DT[x_dtype], _ID2DT[stat_dtype]
+        g = _view(gy, N * C * HW, xdt).reshape(N, C, HW)
+        xs = _view(x, N * C * HW, xdt).reshape(N, C, HW)
+        _view(gx, N * C * HW, xdt).reshape(N, C, HW)[...] = og.bn_bwd_apply(
+            g, xs, _view(mean, C, sdt), _view(inv_std, C, sdt), _view(gamma, C, sdt),
+            _view(ggamma, C, sdt), _view(gbeta, C, sdt), inv_m)
         return 0
 
     # ---------------------------------------------------------------- NCCL --
