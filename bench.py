@@ -990,7 +990,33 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
                     'parameters, gradients and MomentumSGD state'.format(len(named), n_params, batch),
            'batch_per_gpu': batch, 'steps': steps}
 
-    def run(mode):
+    # forward + backward captured ONCE into a CUDA graph (static input, gradients written into
+    # the same arrays at every replay): the stand-in then costs device time only, instead of
+    # ~10 ms of framework host overhead per step that would hide the path being measured
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                for _, p in named:
+                    p.grad = None
+                fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for _, p in named:
+            p.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = fwd_bwd()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(static_loss).item())
+    except Exception as e:      # noqa: BLE001 -- eager numbers below still stand
+        graph = None
+        out['graph_error'] = '%s: %s' % (type(e).__name__, e)
+
+    def run(mode, graphed):
         model = link_from_named_arrays([('/' + nm, p.data) for nm, p in named])
         plink = [p for _, p in sorted(model.namedparams())]
         tparam = [p for _, p in sorted((('/' + nm), p) for nm, p in named)]
@@ -1000,14 +1026,16 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
         opt.setup(model)
 
         def one(update=True):
-            for tp in tparam:
-                tp.grad = None                            # cleargrads(): new gradient arrays
-            loss = fwd_bwd()
+            if graphed:
+                graph.replay()
+            else:
+                for tp in tparam:
+                    tp.grad = None                        # cleargrads(): new gradient arrays
+                fwd_bwd()
             if update:
                 for lp, tp in zip(plink, tparam):
                     lp.grad = tp.grad
                 opt.update()
-            return loss
         for _ in range(warmup):
             one(mode != 'fwd_bwd')
         torch.cuda.synchronize()
@@ -1016,7 +1044,7 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            loss = one(mode != 'fwd_bwd')
+            one(mode != 'fwd_bwd')
         e1.record()
         torch.cuda.synchronize()
         if hasattr(opt, 'wait'):
@@ -1026,19 +1054,31 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
             t = torch.tensor([ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        assert bool(torch.isfinite(loss).item())
+        assert bool(torch.isfinite(next(iter(net.parameters()))).all().item())
         return ms
-    fb = run('fwd_bwd')
-    sync = run('sync')
-    out.update({'fwd_bwd_ms': fb, 'step_ms': sync, 'gradpath_ms': sync - fb,
-                'gradpath_share': (sync - fb) / sync, 'img_per_s': batch * world / (sync * 1e-3),
-                'img_per_s_fwd_bwd_only': batch * world / (fb * 1e-3)})
-    try:
-        db = run('double_buffering')
-        out.update({'step_ms_double_buffering': db,
-                    'img_per_s_double_buffering': batch * world / (db * 1e-3)})
-    except Exception as e:      # noqa: BLE001
-        out['double_buffering_error'] = '%s: %s' % (type(e).__name__, e)
+
+    def leg(graphed, suffix):
+        fb = run('fwd_bwd', graphed)
+        sync = run('sync', graphed)
+        res = {'fwd_bwd_ms' + suffix: fb, 'step_ms' + suffix: sync, 'gradpath_ms' + suffix: sync - fb,
+               'gradpath_share' + suffix: (sync - fb) / sync,
+               'img_per_s' + suffix: batch * world / (sync * 1e-3),
+               'img_per_s_fwd_bwd_only' + suffix: batch * world / (fb * 1e-3)}
+        if not graphed:
+            try:
+                db = run('double_buffering', graphed)
+                res.update({'step_ms_double_buffering' + suffix: db,
+                            'img_per_s_double_buffering' + suffix: batch * world / (db * 1e-3)})
+            except Exception as e:      # noqa: BLE001
+                res['double_buffering_error'] = '%s: %s' % (type(e).__name__, e)
+        return res
+    if graph is not None:
+        out.update(leg(True, ''))
+        out['fwd_bwd'] = 'CUDA graph replay (device-bound)'
+        out.update(leg(False, '_eager'))
+    else:
+        out.update(leg(False, ''))
+        out['fwd_bwd'] = 'eager (host-bound)'
     return out
 
 

@@ -133,6 +133,13 @@ PROTOTYPES = {
                                       c_double, c_double, c_double, c_double, c_double, c_double,
                                       c_double, c_double, c_double, c_int, c_int, c_int,
                                       c_void_p, c_void_p]),
+    'gp_unpack_momentum_sgd_master': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
+                                              c_int64, c_double, c_double, c_double, c_int,
+                                              c_void_p, c_void_p, c_void_p]),
+    'gp_unpack_adam_master': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                      c_double, c_double, c_double, c_double, c_double, c_double,
+                                      c_double, c_double, c_double, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p]),
     'gp_unpack_sgd_family': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                      c_double, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                      c_void_p]),
@@ -188,7 +195,8 @@ KERNEL_FUNCS = frozenset([
     'gp_p2p_allreduce', 'gp_p2p_allreduce_small', 'gp_mc_allreduce',
     'gp_unpack_momentum_sgd_hooked', 'gp_unpack_adam_hooked', 'gp_sqnorm', 'gp_scale_by_device',
     'gp_weight_decay', 'gp_divide', 'gp_unpack_sgd_family', 'gp_step_momentum_sgd', 'gp_step_adam',
-    'gp_bn_fwd_stats_allreduce', 'gp_bn_bwd_stats_allreduce', 'gp_bn_fwd_apply', 'gp_bn_bwd_apply'])
+    'gp_bn_fwd_stats_allreduce', 'gp_bn_bwd_stats_allreduce', 'gp_bn_fwd_apply', 'gp_bn_bwd_apply',
+    'gp_unpack_momentum_sgd_master', 'gp_unpack_adam_master'])
 
 # functions whose int return value is an error code
 _NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',

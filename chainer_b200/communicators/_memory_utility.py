@@ -88,12 +88,18 @@ class ParamsData(object):
     def attach(self, extra_ptrs):
         """extra_ptrs: list (one per param) of (data_array, [state arrays...])."""
         segs = self.host_segs
-        for i, (data, states) in enumerate(extra_ptrs):
+        for i, item in enumerate(extra_ptrs):
+            data, states = item[0], item[1]
             segs['ptr'][i, 1] = _dev.device_ptr(data)
             segs['dtype1'][i] = _dev.dtype_id(_dev.array_dtype(data))
             for k, s in enumerate(states):
                 segs['ptr'][i, 2 + k] = _dev.device_ptr(s)
-            self.arrays.append((data, states))
+            if len(item) > 2:
+                # float32 master weights: ptr[4] is the float16 parameter array behind the
+                # master in ptr[1] (csrc/gp_master.cu); aligned to 4 of ITS elements
+                segs['ptr'][i, 4] = _dev.device_ptr(item[2])
+                self._aux4_align = 8
+            self.arrays.append(item)
 
     def _finish_flags(self):
         segs, csum = self.host_segs, self.host_csum
@@ -108,8 +114,10 @@ class ParamsData(object):
         a0 = np.minimum(isz0 * 4, 16).astype(np.uint64)
         a1 = np.minimum(isz1 * 4, 16).astype(np.uint64)
         ok &= (segs['ptr'][:, 0] % a0) == 0
-        for k in range(1, 5):
+        for k in range(1, 4):
             ok &= (segs['ptr'][:, k] % a1) == 0
+        aux = getattr(self, '_aux4_align', None)
+        ok &= (segs['ptr'][:, 4] % (a1 if aux is None else np.uint64(aux))) == 0
         segs['flags'] = np.where(ok, _lib.GP_SEG_VEC_OK, 0).astype(np.uint32)
         # layout promise for the TMA-staged kernels (include/gradpath.h "layout_hint"):
         # uniform float32 arrays, 16-byte aligned pointers, offsets multiple of 8

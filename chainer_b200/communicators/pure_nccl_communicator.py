@@ -531,9 +531,13 @@ class _FusedPlan(object):
         self.cacheable = bool(getattr(model, '_b200_versioned', False) and
                               getattr(optimizer, '_b200_versioned', False) and
                               all(getattr(r, '_b200_versioned', False) for r in self.rules))
-        # states are created on first use (chainer/optimizer.py:473-484)
+        self.master = bool(_is_master_plan(self.params))
+        self.skip_flag = None                # device word of the dynamic-loss-scaling check
+        # states are created on first use (chainer/optimizer.py:473-484); with float32
+        # master weights on the float32 copy of the parameter (:262-282)
         for p in self.params:
-            p.update_rule._init_states(p)
+            rule = p.update_rule
+            rule._init_states(rule.fp32_param_for(p) if self.master else p)
         self.versions = _versions()          # after state creation
         for p in self.params:                # ParamsData zero_fill (_memory_utility.py:40-42)
             if p.grad is None:
@@ -541,7 +545,11 @@ class _FusedPlan(object):
         self.extra = []
         for p in self.params:
             st = p.update_rule.state
-            self.extra.append((p.data, [st[k] for k in p.update_rule.state_names]))
+            states = [st[k] for k in p.update_rule.state_names]
+            if self.master:
+                self.extra.append((p.update_rule._fp32_param.data, states, p.data))
+            else:
+                self.extra.append((p.data, states))
         self.table = _memory_utility.DeviceTable()
         self.pd = _memory_utility.ParamsData(self.params, 'grad', False, extra_ptrs=self.extra,
                                              table=self.table)
@@ -693,9 +701,30 @@ class _FusedPlan(object):
                 rep._check_eps(np.float32 if ddt == np.float16 else ddt.type)
             launches.append((key, t))
 
+        master = self.master
+        dynamic = bool(getattr(self.optimizer, '_loss_scaling_is_dynamic', False))
+        skip_ptr = None
+        if dynamic:
+            # is_safe_to_update() on the device: gp_check_finite over the reduced buffer sets
+            # this word, the master kernels skip on it -- no host decision between the
+            # allreduce and the update (chainer/optimizer.py:763-779)
+            if self.skip_flag is None:
+                self.skip_flag = _dev.DeviceArray.zeros((1,), np.int32)
+            skip_ptr = self.skip_flag.data.ptr
+
         def launch(key, t, begin, end):
             hint = t.layout_hint(dtype)
-            if key[0] == 'momentum_sgd':
+            if master:
+                if key[0] == 'momentum_sgd':
+                    lib.gp_unpack_momentum_sgd_master(buf_ptr, buf_id, t.d_csum, t.d_segs,
+                                                      t.n_params, begin, end, scale, key[1], key[2],
+                                                      wg, hk_addr, skip_ptr, sp)
+                else:
+                    lib.gp_unpack_adam_master(buf_ptr, buf_id, t.d_csum, t.d_segs, t.n_params,
+                                              begin, end, scale, key[1], key[2], key[3], key[4],
+                                              key[5], key[6], key[7], key[8], key[9], wg, hk_addr,
+                                              skip_ptr, sp)
+            elif key[0] == 'momentum_sgd':
                 if hooked:
                     lib.gp_unpack_momentum_sgd_hooked(buf_ptr, buf_id, t.d_csum, t.d_segs,
                                                       t.n_params, begin, end, scale, key[1],
@@ -715,15 +744,21 @@ class _FusedPlan(object):
                                    scale, key[1], key[2], key[3], key[4], key[5], key[6], key[7],
                                    key[8], key[9], wg, hint, sp)
 
-        if clip is not None:
-            # the global norm needs every bucket reduced: one reduction over the whole
-            # allreduced buffer forms the rate on the device, then the update(s) run
-            threshold = float(clip.threshold)
-            sc = clip.scratch()
+        if clip is not None or dynamic:
+            # the global norm (and the finiteness verdict) need every bucket reduced: one
+            # reduction over the whole allreduced buffer forms the rate (sets the skip word)
+            # on the device, then the update(s) run
+            threshold = float(clip.threshold) if clip is not None else 0.0
+            sc = clip.scratch() if clip is not None else None
 
             def consume(begin, end):
                 if end == n_elems:
-                    lib.gp_sqnorm(buf_ptr, buf_id, n_elems, scale, 0, threshold, sc.ws, sc.out, sp)
+                    if dynamic:
+                        lib.gp_memset_async(skip_ptr, 0, 4, sp)
+                        lib.gp_check_finite(buf_ptr, buf_id, n_elems, skip_ptr, sp)
+                    if clip is not None:
+                        lib.gp_sqnorm(buf_ptr, buf_id, n_elems, scale, 0, threshold, sc.ws, sc.out,
+                                      sp)
                     for key, t in launches:
                         launch(key, t, 0, t.n_elems)
         elif len(launches) == 1:
@@ -738,12 +773,53 @@ class _FusedPlan(object):
                 if end == n_elems:
                     for key, t in launches:
                         launch(key, t, 0, t.n_elems)
-        if (not hooked and len(launches) == 1 and not config.is_debug() and
+        if (not hooked and not master and len(launches) == 1 and not config.is_debug() and
                 self._run_step(lib, launches[0][0], launches[0][1], dtype, buf_id, scale, wg,
                                n_elems, stream)):
             return True
         comm._pipeline(pd, dtype, stream, consume)
+        if dynamic:
+            self._finish_dynamic_loss_scale(stream)
         return True
+
+    def _finish_dynamic_loss_scale(self, stream):
+        """The host half of dynamic loss scaling, AFTER the whole step is enqueued: read the
+        4-byte verdict (the only synchronisation of the step, at its end -- the reference
+        synchronises per parameter before it may launch the updates), undo the step counters
+        of a skipped update, warn like ``check_nan_in_grads`` and move the scale
+        (``chainer/optimizer.py:763-791``)."""
+        import warnings
+        opt = self.optimizer
+        bad = int(self.skip_flag.get(stream)[0]) != 0
+        opt._loss_scaling_isnan = bad
+        if bad:
+            opt._loss_scaling_isnan_ever = True
+            for rule in self.rules:          # param.update() was not called
+                rule.t -= 1
+            for rule in self.other_rules:
+                rule.t -= 1
+            names = self._nonfinite_names()
+            for name in names or ['(the reduced gradient buffer)']:
+                warnings.warn(
+                    'Non finite number found in param.grad of {}'
+                    ' (iteration: {}, loss_scale: {})'
+                    .format(name, opt.t - 1, opt._loss_scale))
+        opt.update_loss_scale()
+
+    def _nonfinite_names(self):
+        """Names of the parameters whose (mean) gradient is not finite -- only run after a
+        skipped step, to word the warning like the reference."""
+        lib = _lib.get()
+        named = [(n, p) for n, p in sorted(self.model.namedparams()) if p.grad is not None]
+        if not named or not self.comm.write_grad:
+            return []
+        flags = _dev.DeviceArray.zeros((len(named),), np.int32)
+        for i, (_, p) in enumerate(named):
+            g = p.grad
+            lib.gp_check_finite(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
+                                _dev.array_size(g), flags.data.ptr + 4 * i, 0)
+        host = flags.get()
+        return [n for (n, _), b in zip(named, host) if b]
 
     def _run_step(self, lib, key, t, dtype, buf_id, scale, wg, n_elems, stream):
         """The whole step as ONE launch (csrc/gp_step.cu) when it covers this
@@ -837,11 +913,30 @@ def _fusable_hooks(optimizer):
     return None
 
 
+def _is_master_plan(params):
+    """True: every parameter is float16 with use_fp32_update and a rule the master kernels
+    cover; False: none uses fp32 update; None: a mixture or an uncovered rule (not fusable)."""
+    flags = []
+    for p in params:
+        rule = getattr(p, 'update_rule', None)
+        flags.append(bool(rule is not None and rule._use_fp32_update and p.data is not None and
+                          _dev.array_dtype(p.data) == np.float16))
+    if not any(flags):
+        return False
+    if not all(flags):
+        return None
+    for p in params:
+        rule = p.update_rule
+        if getattr(rule, 'fused_kind', None) not in ('momentum_sgd', 'adam'):
+            return None
+        if rule.fused_kind == 'adam' and rule.hyperparam.amsgrad:
+            return None
+    return True
+
+
 def _fusion_plan(model, optimizer, zero_fill):
     """Decide whether ``optimizer.update(None)`` can be fused; returns
     (params_in_layout_order, other_params) or None."""
-    if getattr(optimizer, '_loss_scaling_is_dynamic', False):
-        return None                       # needs the NaN check + host decision every step
     if _fusable_hooks(optimizer) is None:
         return None
     if getattr(optimizer, 'target', None) is not model:
@@ -849,11 +944,20 @@ def _fusion_plan(model, optimizer, zero_fill):
     params = _memory_utility.extract_params_set_grad(model, zero_fill)
     chosen = set(id(p) for p in params)
     others = [p for p in model.params() if id(p) not in chosen]
+    # float32 master weights behind float16 parameters (use_fp32_update): fused when EVERY
+    # parameter of the step is such a pair and the rule is MomentumSGD or Adam (gp_master.cu)
+    master = _is_master_plan(params)
+    if master is None:
+        return None
+    if getattr(optimizer, '_loss_scaling_is_dynamic', False) and not master:
+        # dynamic loss scaling is fused with the master-weight kernels only (float16
+        # training); elsewhere the reference sequence runs
+        return None
     for p in params:
         rule = getattr(p, 'update_rule', None)
         if rule is None or getattr(rule, 'fused_kind', None) is None:
             return None
-        if not rule.enabled or rule._use_fp32_update or rule._hookable.has_hooks():
+        if not rule.enabled or rule._hookable.has_hooks():
             return None
         ddt = _dev.array_dtype(p.data)
         if isinstance(ddt, str) or ddt not in (np.float16, np.float32, np.float64):

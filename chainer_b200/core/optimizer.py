@@ -189,13 +189,8 @@ class UpdateRule(object):
         if self._use_fp32_update and is_initialized and param.dtype == np.float16:
             # fp32 master weights (``optimizer.py:262-282``): the update runs on a
             # float32 copy of the parameter with the gradient up-cast to float32
-            from chainer_b200.core import link as _link
             from chainer_b200.core.optimizers import _single
-            if self._fp32_param is None:
-                master = _single.new_like(param.data, np.float32)
-                _single.cast_copy(master, param.data)
-                self._fp32_param = _link.Parameter(master, name=param.name)
-            fp32_param = self._fp32_param
+            fp32_param = self.fp32_param_for(param)
             if param.grad is not None:
                 g32 = _single.new_like(param.grad, np.float32)
                 _single.cast_copy(g32, param.grad)
@@ -220,6 +215,17 @@ class UpdateRule(object):
             from chainer_b200.core.optimizers import _single
             _single.cast_copy(param.data, param_.data)
             param_.grad = None
+
+    def fp32_param_for(self, param):
+        """The float32 master copy of a float16 parameter, created on first use
+        (``optimizer.py:262-273``)."""
+        if self._fp32_param is None:
+            from chainer_b200.core import link as _link
+            from chainer_b200.core.optimizers import _single
+            master = _single.new_like(param.data, np.float32)
+            _single.cast_copy(master, param.data)
+            self._fp32_param = _link.Parameter(master, name=param.name)
+        return self._fp32_param
 
     def update_core(self, param):
         self.update_core_gpu(param)

@@ -244,6 +244,38 @@ int launch(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t be
 #undef GP_LAUNCH
 }
 
+// Ops that only exist for all-float32 parameter arrays (PT = GP_F32: no dtype dispatch,
+// no generic scalar path): the three scale modes, the op's default unroll.
+template <class Op, class B>
+int launch_f32(const int64_t* d_csum, const gp_seg_t* d_segs, int n_segs, int64_t begin,
+               int64_t end, const Op& op, void* stream, const char* what) {
+  if (n_segs <= 0 || end <= begin) return 0;
+  if (begin < 0 || (begin & 3)) {
+    gp_set_error("%s: elem_begin (%lld) must be a non-negative multiple of 4", what,
+                 (long long)begin);
+    return GP_EINVAL;
+  }
+  const GpTuning& t = g_gp_tuning;
+  int threads = t.threads < 32 ? 32 : (t.threads > kMaxThreads ? kMaxThreads : t.threads);
+  threads &= ~31;
+  WalkArgs a;
+  a.csum = d_csum;
+  a.segs = d_segs;
+  a.n_segs = n_segs;
+  a.use_smem = n_segs <= kMaxSmemSegs;
+  a.begin = begin;
+  a.end = end;
+  a.per_cta = 0;
+  const size_t smem = a.use_smem ? (size_t)(n_segs + 1) * sizeof(int64_t) : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int U = Op::kDefaultUnroll;
+  switch (op.s.mode) {
+    case 0: return launch_u<Op, B, U, 0, GP_F32>(a, op, threads, smem, st, what);
+    case 1: return launch_u<Op, B, U, 1, GP_F32>(a, op, threads, smem, st, what);
+    default: return launch_u<Op, B, U, 2, GP_F32>(a, op, threads, smem, st, what);
+  }
+}
+
 // dispatch on the runtime buffer dtype
 // f32: the caller promises that every segment's arrays are float32 (layout_hint)
 template <class Op>

@@ -369,6 +369,30 @@ int gp_unpack_adam_hooked(const void* buffer, int buf_dtype, const int64_t* d_cs
                           double weight_decay_rate, double lower, double upper, int adam_flags,
                           int write_grad, int layout_hint, const gp_hooks_t* hooks, void* stream);
 
+/* float16 parameters with FLOAT32 MASTER WEIGHTS (csrc/gp_master.cu): ONE launch replaces, per
+ * parameter, `fp32_param.grad = param.grad.astype(float32)`, `grad /= loss_scale`,
+ * update_core_gpu on the float32 copy and `param.array = fp32_param.array.astype(float16)`
+ * (chainer/optimizer.py:262-305), with the optimizer-level hooks (acting on the float16
+ * arrays, as the reference's do) and the dynamic-loss-scaling skip fused in.
+ * Tables: ptr[0] float16 gradient (with write_grad it receives the mean gradient after the
+ * hooks), ptr[1] float32 master, ptr[2..3] float32 states, ptr[4] float16 parameter;
+ * dtype0 = GP_F16, dtype1 = GP_F32.  hooks may be NULL.  d_skip may be NULL; else a device
+ * int32 (gp_check_finite over the reduced buffer): non-zero = a non-finite gradient, nothing
+ * is updated (`is_safe_to_update()`, chainer/optimizer.py:763-779, without a host round trip
+ * between the allreduce and the update).  AMSGrad is not covered. */
+int gp_unpack_momentum_sgd_master(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                                  const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                                  int64_t elem_end, double scale, double lr, double momentum,
+                                  int write_grad, const gp_hooks_t* hooks, const void* d_skip,
+                                  void* stream);
+int gp_unpack_adam_master(const void* buffer, int buf_dtype, const int64_t* d_csum,
+                          const gp_seg_t* d_segs, int n_segs, int64_t elem_begin,
+                          int64_t elem_end, double scale, double alpha_t, double one_minus_beta1,
+                          double one_minus_beta2, double eps, double eta,
+                          double weight_decay_rate, double lower, double upper, int adam_flags,
+                          int write_grad, const gp_hooks_t* hooks, const void* d_skip,
+                          void* stream);
+
 /* The other first-order rules with MomentumSGD's shape (csrc/gp_sgd_family.cu), same
  * tables (ptr[0] grad, ptr[1] param, ptr[2] v), hooks optional (NULL: none):
  *   GP_RULE_SGD                 param -= lr * grad                  chainer/optimizers/sgd.py:45-63

@@ -355,6 +355,64 @@ class FakeLib(object):
                 _view(int(segs['ptr'][j, 0]), size, pdt)[e0:e1] = g
         return 0
 
+    # -- float32 master weights (csrc/gp_master.cu) ------------------------------------
+    def _master(self, kind, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, write_grad,
+                hooks, d_skip, update):
+        csum, segs = self._tables_of(d_csum, d_segs, n)
+        skip = bool(d_skip) and int(_view(d_skip, 1, np.int32)[0]) != 0
+        h = _lib.GpHooks.from_address(int(hooks)) if hooks else None
+        f16, f32 = np.dtype(np.float16), np.dtype(np.float32)
+        for j, e0, e1 in self._pieces(csum, n, begin, end):
+            assert int(segs['dtype0'][j]) == 6 and int(segs['dtype1'][j]) == 7
+            size = int(csum[j + 1] - csum[j])
+            g16 = self._mean_grad(buffer, buf_dtype, int(segs['buf_off'][j]), e0, e1, scale, f16,
+                                  segs[j], size)
+            g16 = np.array(g16)
+            gout = _view(int(segs['ptr'][j, 0]), size, f16)[e0:e1]
+            if skip:
+                if write_grad:
+                    gout[...] = g16
+                continue
+            p32 = _view(int(segs['ptr'][j, 1]), size, f32)[e0:e1]
+            p16 = _view(int(segs['ptr'][j, 4]), size, f16)[e0:e1]
+            if h is not None and h.clip_rate:
+                g16 *= f16.type(_view(h.clip_rate, 1, np.float32)[0])
+            if h is not None and h.weight_decay != 0.0:
+                og.weight_decay_hook(p32.astype(f16), g16, h.weight_decay)
+            g32 = g16.astype(f32)
+            if h is not None and h.loss_scale != 0.0:
+                og.loss_scale_divide(g32, h.loss_scale)
+            update(segs, j, size, e0, e1, p32, g32)
+            p16[...] = p32.astype(f16)
+            if write_grad:
+                gout[...] = g16
+
+    def gp_unpack_momentum_sgd_master(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale,
+                                      lr, momentum, write_grad, hooks, d_skip, stream):
+        self.calls.append(('gp_unpack_momentum_sgd_master', (buf_dtype, n, begin, end, scale, lr,
+                                                             momentum, write_grad)))
+
+        def update(segs, j, size, e0, e1, p32, g32):
+            v = _view(int(segs['ptr'][j, 2]), size, np.float32)[e0:e1]
+            og.momentum_sgd_update(p32, g32, v, lr, momentum)
+        self._master('sgd', buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, write_grad, hooks,
+                     d_skip, update)
+        return 0
+
+    def gp_unpack_adam_master(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, alpha_t,
+                              omb1, omb2, eps, eta, wd, lower, upper, flags, write_grad, hooks,
+                              d_skip, stream):
+        self.calls.append(('gp_unpack_adam_master', (buf_dtype, n, begin, end, scale, alpha_t, flags,
+                                                     write_grad)))
+
+        def update(segs, j, size, e0, e1, p32, g32):
+            m = _view(int(segs['ptr'][j, 2]), size, np.float32)[e0:e1]
+            v = _view(int(segs['ptr'][j, 3]), size, np.float32)[e0:e1]
+            _adam_kernel(p32, g32, m, v, None, alpha_t, omb1, omb2, eps, eta, wd, lower, upper, flags)
+        self._master('adam', buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, write_grad, hooks,
+                     d_skip, update)
+        return 0
+
     def gp_unpack_sgd_family(self, buffer, buf_dtype, d_csum, d_segs, n, begin, end, scale, rule,
                              lr, momentum, write_grad, layout_hint, hooks, stream):
         self.calls.append(('gp_unpack_sgd_family', (buf_dtype, n, begin, end, scale, rule, lr,
@@ -421,6 +479,7 @@ class FakeLib(object):
         return 0
 
     def gp_check_finite(self, buffer, dtype, n, d_flag, stream):
+        self.calls.append(('gp_check_finite', (dtype, n)))
         if not np.isfinite(_buf_read(buffer, n, dtype)).all():
             _view(d_flag, 1, np.int32)[0] |= 1
         return 0

@@ -272,6 +272,52 @@ def make_dynamic_loss_scale():
     print('dynamic_loss_scale', len(out), out['float32|scales'], out['float32|t'])
 
 
+def make_fp32_dynamic():
+    """float16 parameters, float32 master weights AND dynamic loss scaling together (the
+    float16 training recipe; chainer/optimizer.py:262-305, 736-791, 857-894): MomentumSGD
+    with WeightDecay, and Adam; 6 steps, a non-finite gradient in step 2.  Records the scaled
+    gradients fed in, the float16 parameters, the float32 masters, the loss scales and t."""
+    from chainer import optimizer_hooks as H
+    out = {}
+    cases = {
+        'sgd_wd': (lambda: optimizers.MomentumSGD(lr=0.01, momentum=0.9), [H.WeightDecay(0.05)], 1e-2),
+        'adam': (lambda: optimizers.Adam(), [], 0.5),
+    }
+    dt = np.dtype('float16')
+    for case, (mk, hooks, gs) in cases.items():
+        rng = np.random.default_rng(37)
+        net = _Net(SHAPES, dt, rng)
+        opt = mk()
+        opt.use_fp32_update()
+        opt.setup(net)
+        for h in hooks:
+            opt.add_hook(h)
+        opt.loss_scaling(interval=2)
+        for n, p in sorted(net.namedparams()):
+            out['%s|init%s' % (case, n)] = p.data.copy()
+        scales = []
+        for step in range(6):
+            ls = opt._loss_scale
+            for n, p in sorted(net.namedparams()):
+                g = np.asarray(rng.standard_normal(p.shape) * gs).astype(dt).reshape(p.shape)
+                if step == 2 and n == '/p03':
+                    g[5] = np.inf
+                out['%s|grad%d%s' % (case, step, n)] = g.copy()        # unscaled
+                p.grad = np.asarray(g * dt.type(ls)).astype(dt).reshape(p.shape)
+                p._loss_scale = ls
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                opt.update()
+            scales.append(opt._loss_scale)
+            for n, p in sorted(net.namedparams()):
+                out['%s|param%d%s' % (case, step, n)] = p.data.copy()
+                out['%s|master%d%s' % (case, step, n)] = p.update_rule._fp32_param.data.copy()
+        out['%s|scales' % case] = np.asarray(scales, dtype=np.float64)
+        out['%s|t' % case] = np.asarray([opt.t] + [p.update_rule.t for _, p in sorted(net.namedparams())])
+    np.savez_compressed(os.path.join(HERE, 'fp32_dynamic.npz'), **out)
+    print('fp32_dynamic', len(out), out['sgd_wd|scales'], out['sgd_wd|t'])
+
+
 ADAM_VARIANTS = {
     'adam': dict(),
     'adamw': dict(eta=0.5, weight_decay_rate=0.1),
@@ -409,3 +455,4 @@ if __name__ == '__main__':
     make_sgd_family()
     make_dynamic_loss_scale()
     make_fp32_update()
+    make_fp32_dynamic()

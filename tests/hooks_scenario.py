@@ -209,3 +209,71 @@ def run_fp32_update(case, multi_node, to_arr, to_np):
     assert actual.t == 3
     if comm is not None:
         comm.finalize()
+
+
+def run_fp32_dynamic(case, multi_node, to_arr, to_np, fake=None):
+    """fp32_dynamic.npz (generated from the unmodified reference): float16 parameters,
+    float32 master weights and DYNAMIC loss scaling together; step 2 carries a non-finite
+    gradient -> update skipped, scale halved, step counters of the rules not advanced.
+    Behind the multi-node optimizer this is the fused master path (gp_unpack_*_master with
+    the device-side skip word)."""
+    import warnings
+    z = _npz('fp32_dynamic.npz')
+    pre = case + '|'
+    dt = np.dtype(np.float16)
+    names = sorted(k[len(pre) + 4:] for k in z.files if k.startswith(pre + 'init'))
+    model = L.link_from_named_arrays([(n, to_arr(z[pre + 'init' + n])) for n in names])
+    actual = chainer_b200.MomentumSGD(lr=0.01, momentum=0.9) if case == 'sgd_wd' \
+        else chainer_b200.Adam()
+    actual.use_fp32_update()
+    comm = None
+    if multi_node:
+        comm = chainer_b200.create_communicator('pure_nccl', allreduce_grad_dtype=np.float16)
+        opt = chainer_b200.create_multi_node_optimizer(actual, comm)
+    else:
+        opt = actual
+    opt.setup(model)
+    if case == 'sgd_wd':
+        from chainer_b200 import optimizer_hooks as H
+        opt.add_hook(H.WeightDecay(0.05))
+    actual.loss_scaling(interval=2)
+    if multi_node:
+        opt.update()
+    params = dict(sorted(model.namedparams()))
+    exact = case == 'sgd_wd'            # Adam: GPU formula here, CPU formula in the vectors
+    scales = []
+    for step in range(6):
+        ls = actual._loss_scale
+        for n in names:
+            g = z[pre + 'grad%d%s' % (step, n)]
+            params[n].grad = to_arr(np.asarray(g * dt.type(ls)).astype(dt).reshape(g.shape))
+            params[n]._loss_scale = ls
+        if fake is not None:
+            fake.calls[:] = []
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter('always')
+            opt.update()
+        assert any('Non finite number found in param.grad of /p03' in str(x.message)
+                   for x in w) == (step == 2)
+        if fake is not None and multi_node:
+            called = [c[0] for c in fake.calls]
+            kernel = 'gp_unpack_momentum_sgd_master' if case == 'sgd_wd' else 'gp_unpack_adam_master'
+            assert kernel in called and 'gp_check_finite' in called, called
+            assert 'gp_divide' not in called and 'gp_weight_decay' not in called
+        scales.append(actual._loss_scale)
+        for n in names:
+            want_p, want_m = z[pre + 'param%d%s' % (step, n)], z[pre + 'master%d%s' % (step, n)]
+            got_p = to_np(params[n].data).reshape(want_p.shape)
+            got_m = to_np(params[n].update_rule._fp32_param.data).reshape(want_m.shape)
+            if exact:
+                assert_bits_equal(got_m, want_m, (case, step, n, 'master'))
+                assert_bits_equal(got_p, want_p, (case, step, n))
+            else:
+                np.testing.assert_allclose(got_m, want_m, rtol=2e-5, atol=1e-7)
+                np.testing.assert_allclose(got_p.astype(np.float32), want_p.astype(np.float32),
+                                           rtol=2e-3, atol=1e-6)
+    np.testing.assert_array_equal(np.asarray(scales, dtype=np.float64), z[pre + 'scales'])
+    ts = [actual.t] + [p.update_rule.t for _, p in sorted(model.namedparams())]
+    np.testing.assert_array_equal(np.asarray(ts), z[pre + 't'])
+    if comm is not None:
+        comm.finalize()

@@ -20,6 +20,11 @@ def _tol(dtype):
     return {'float32': 2e-6, 'float16': 2e-3, 'float64': 1e-12}[dtype]
 
 
+def _floor(dtype):
+    """Absolute floor: the spacing of the output type's subnormals (float16: 6e-8)."""
+    return {'float32': 1e-30, 'float16': 1e-7, 'float64': 1e-300}[dtype]
+
+
 @pytest.mark.parametrize('dtype', ['float32', 'float16', 'float64'])
 @pytest.mark.parametrize('shape', SHAPES, ids=[str(s) for s in SHAPES])
 @pytest.mark.parametrize('with_running', [False, True])
@@ -51,8 +56,8 @@ def test_bn_fwd_apply(dtype, shape, with_running):
     mag = np.abs(gamma.reshape(sh) * (x64 - mean.reshape(sh)) * istd64.reshape(sh)) + np.abs(beta.reshape(sh))
     t = _tol(dtype)
     got = to_host(y).astype(np.float64)
-    assert np.all(np.abs(got - y64) <= 4 * t * mag + 1e-30), float(np.abs(got - y64).max())
-    assert np.all(np.abs(got - want.astype(np.float64)) <= 2 * t * mag + 1e-30)
+    assert np.all(np.abs(got - y64) <= 4 * t * mag + _floor(dtype)), float(np.abs(got - y64).max())
+    assert np.all(np.abs(got - want.astype(np.float64)) <= 2 * t * mag + _floor(dtype))
     np.testing.assert_allclose(to_host(inv_std), istd64, rtol=2e-7 if sdt is np.float32 else 1e-15)
     if with_running:
         og.bn_running_update(rm, rv, mean, var, decay, adjust)
@@ -90,8 +95,8 @@ def test_bn_bwd_apply(dtype, shape):
     mag = np.abs((gamma * inv_std).reshape(sh)) * (np.abs(g64) + np.abs(t64))
     t = _tol(dtype)
     got = to_host(gx).astype(np.float64)
-    assert np.all(np.abs(got - gx64) <= 6 * t * mag + 1e-30), float(np.abs(got - gx64).max())
-    assert np.all(np.abs(got - want.astype(np.float64)) <= 2 * t * mag + 1e-30)
+    assert np.all(np.abs(got - gx64) <= 6 * t * mag + _floor(dtype)), float(np.abs(got - gx64).max())
+    assert np.all(np.abs(got - want.astype(np.float64)) <= 2 * t * mag + _floor(dtype))
 
 
 @pytest.mark.parametrize('shape', [(8, 32, 14, 14), (4, 6, 5, 5)])

@@ -317,3 +317,12 @@ def test_dynamic_loss_scaling_gpu(dtype, multi_node):
 def test_fp32_master_weights_gpu(case, multi_node):
     from tests.hooks_scenario import run_fp32_update
     run_fp32_update(case, multi_node, lambda a: to_dev(np.array(a)), to_host)
+
+
+@pytest.mark.parametrize('case', ['sgd_wd', 'adam'])
+@pytest.mark.parametrize('multi_node', [False, True])
+def test_fp32_master_with_dynamic_loss_scaling_gpu(case, multi_node):
+    """float16 parameters + float32 masters + dynamic loss scaling against the reference's
+    vectors (fp32_dynamic.npz): the fused master kernels with the device-side skip word."""
+    from tests.hooks_scenario import run_fp32_dynamic
+    run_fp32_dynamic(case, multi_node, lambda a: to_dev(np.array(a)), to_host)

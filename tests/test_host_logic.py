@@ -844,3 +844,26 @@ def test_one_launch_step_not_taken_with_hooks(fake, monkeypatch):
     actual_opt.update()
     names = [c[0] for c in fake.calls]
     assert 'gp_unpack_momentum_sgd_hooked' in names and 'gp_pack' in names
+
+
+@pytest.mark.parametrize('case', ['sgd_wd', 'adam'])
+@pytest.mark.parametrize('multi_node', [False, True])
+def test_fp32_master_with_dynamic_loss_scaling(fake, case, multi_node):
+    """float16 parameters + float32 masters + dynamic loss scaling against vectors of the
+    unmodified reference (fp32_dynamic.npz); behind the multi-node optimizer through the
+    fused master kernels with the device-side skip word."""
+    from tests.hooks_scenario import run_fp32_dynamic
+    run_fp32_dynamic(case, multi_node, lambda a: a.copy(), np.asarray, fake=fake)
+
+
+@pytest.mark.parametrize('case', ['sgd', 'sgd_wd_ls128', 'adam'])
+def test_fp32_master_multi_node_is_fused(fake, case):
+    """use_fp32_update behind create_multi_node_optimizer: ONE master launch per step, none of
+    the per-parameter cast / divide / update launches."""
+    from tests.hooks_scenario import run_fp32_update
+    run_fp32_update(case, True, lambda a: a.copy(), np.asarray)
+    called = [c[0] for c in fake.calls]
+    kernel = 'gp_unpack_adam_master' if case == 'adam' else 'gp_unpack_momentum_sgd_master'
+    assert called.count(kernel) == 3
+    assert 'gp_unpack_momentum_sgd' not in called and 'gp_unpack_adam' not in called
+    assert 'gp_divide' not in called
