@@ -891,24 +891,39 @@ class _TableSet(object):
                 sub.set_ptr0(ptrs[idx], stream)
 
 
+# hook classes the fused kernels implement (chainer_b200.integration adds the reference's)
+WEIGHT_DECAY_HOOKS = ()
+GRADIENT_CLIPPING_HOOKS = ()
+
+
+def _hook_classes():
+    global WEIGHT_DECAY_HOOKS, GRADIENT_CLIPPING_HOOKS
+    if not WEIGHT_DECAY_HOOKS:
+        from chainer_b200 import optimizer_hooks as H
+        WEIGHT_DECAY_HOOKS = (H.WeightDecay,) + tuple(WEIGHT_DECAY_HOOKS)
+        GRADIENT_CLIPPING_HOOKS = (H.GradientClipping,) + tuple(GRADIENT_CLIPPING_HOOKS)
+    return WEIGHT_DECAY_HOOKS, GRADIENT_CLIPPING_HOOKS
+
+
 def _fusable_hooks(optimizer):
     """The optimizer-level hooks as (GradientClipping or None, WeightDecay or None) when
     the fused kernels can apply them in registration order -- no hooks,
     [WeightDecay], [GradientClipping], [GradientClipping, WeightDecay] -- else None
     (other orders, other hooks, 'post' hooks: the reference sequence runs unfused)."""
-    from chainer_b200 import optimizer_hooks as H
+    wd_classes, clip_classes = _hook_classes()
     hookable = getattr(optimizer, '_hookable', None)
     if hookable is None or hookable._post:
         return None
     pre = list(hookable._pre.values())
-    kinds = [type(h) for h in pre]
+    kinds = ['wd' if type(h) in wd_classes else ('clip' if type(h) in clip_classes else '?')
+             for h in pre]
     if not kinds:
         return (None, None)
-    if kinds == [H.WeightDecay]:
+    if kinds == ['wd']:
         return (None, pre[0])
-    if kinds == [H.GradientClipping]:
+    if kinds == ['clip']:
         return (pre[0], None)
-    if kinds == [H.GradientClipping, H.WeightDecay]:
+    if kinds == ['clip', 'wd']:
         return (pre[0], pre[1])
     return None
 
@@ -930,6 +945,8 @@ def _is_master_plan(params):
         if getattr(rule, 'fused_kind', None) not in ('momentum_sgd', 'adam'):
             return None
         if rule.fused_kind == 'adam' and rule.hyperparam.amsgrad:
+            return None
+        if not hasattr(rule, 'fp32_param_for'):
             return None
     return True
 

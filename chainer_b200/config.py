@@ -40,8 +40,16 @@ def get_dtype(dtype=None, map_mixed16=None):
 
 
 def set_dtype(dtype):
-    """Set the global default dtype (None restores CHAINER_DTYPE)."""
+    """Set the global default dtype (None restores CHAINER_DTYPE); with the real ``chainer``
+    imported this is ``chainer.global_config.dtype``."""
     _dtype[0] = dtype
+    ch = _modules.get('chainer')
+    if ch is not None and hasattr(ch, 'global_config'):
+        value = _env_dtype if dtype is None else dtype
+        if isinstance(value, str) and value == mixed16:
+            ch.global_config.dtype = getattr(ch, 'mixed16', np.dtype(np.float16))
+        else:
+            ch.global_config.dtype = np.dtype(value)
 
 
 def is_debug():

@@ -489,6 +489,7 @@ class FakeLib(object):
         return 64
 
     def gp_bn_fwd_stats(self, x, x_dtype, N, C, HW, out, out_dtype, ws, stream):
+        self.calls.append(('gp_bn_fwd_stats', (N, C, HW)))
         xs = _view(x, N * C * HW, _ID2DT[x_dtype]).reshape(N, C, HW)
         _view(out, 2 * C, _ID2DT[out_dtype])[...] = og.bn_fwd_stats(xs, _ID2DT[out_dtype])
         return 0
@@ -499,6 +500,7 @@ class FakeLib(object):
 
     def gp_bn_bwd_stats(self, gy, gy_dtype, xh, x_dtype, mean, inv_std, stat_dtype, N, C, HW, out,
                         out_dtype, ws, stream):
+        self.calls.append(('gp_bn_bwd_stats', (N, C, HW)))
         g = _view(gy, N * C * HW, _ID2DT[gy_dtype]).reshape(N, C, HW)
         x = _view(xh, N * C * HW, _ID2DT[x_dtype]).reshape(N, C, HW)
         if mean and inv_std:
