@@ -1,74 +1,52 @@
-"""Rank discovery and NCCL bootstrap: mirror of
-``chainermn/communicators/_communication_utility.py:9-76, 177-186``."""
-import collections
+"""Rank discovery and NCCL bootstrap over the control plane.
 
+Same results as ``chainermn/communicators/_communication_utility.py:9-76, 177-186``
+(``init_ranks``, ``init_nccl_comm``, ``_get_nccl_type_id``); written for this package's
+control plane: every rank learns all host names with ONE ``allgather`` and derives its own
+five numbers locally (the reference gathers to rank 0, computes everybody's tuple there
+and scatters).
+"""
 import numpy as np
 
 from chainer_b200 import nccl
 from chainer_b200.communicators import _control_plane
 
+_NCCL_IDS = {
+    np.dtype(np.float16): nccl.NCCL_FLOAT16,
+    np.dtype(np.float32): nccl.NCCL_FLOAT32,
+    np.dtype(np.float64): nccl.NCCL_FLOAT64,
+}
+
 
 def init_ranks(mpi_comm):
-    """Returns (rank, intra_rank, intra_size, inter_rank, inter_size), derived
-    from the processor (host) names exactly as the reference does
-    (``_communication_utility.py:9-58``)."""
-    global_names = mpi_comm.gather(_control_plane.get_processor_name())
+    """``(rank, intra_rank, intra_size, inter_rank, inter_size)`` of this process.
 
-    if mpi_comm.rank == 0:
-        name_to_global_ranks = collections.defaultdict(list)
-        for global_rank, name in enumerate(global_names):
-            name_to_global_ranks[name].append(global_rank)
-
-        for global_ranks in name_to_global_ranks.values():
-            global_ranks.sort()
-
-        inter_names = sorted(
-            set(global_names), key=lambda name: name_to_global_ranks[name])
-        name_to_inter_rank = {
-            name: inter_rank
-            for inter_rank, name in enumerate(inter_names)
-        }
-        inter_size = len(inter_names)
-
-        all_ranks = []
-        for global_rank, name in enumerate(global_names):
-            ranks = name_to_global_ranks[name]
-            intra_rank = ranks.index(global_rank)
-            intra_size = len(ranks)
-            inter_rank = name_to_inter_rank[name]
-            all_ranks.append((
-                global_rank, intra_rank, intra_size,
-                inter_rank, inter_size))
-        my_ranks = mpi_comm.scatter(all_ranks)
-    else:
-        my_ranks = mpi_comm.scatter(None)
-
-    assert my_ranks[0] == mpi_comm.rank
-    return my_ranks
+    A *node* is a distinct processor (host) name; nodes are numbered by their lowest
+    global rank, the processes of a node by ascending global rank -- the numbering the
+    reference produces."""
+    me = mpi_comm.rank
+    hosts = mpi_comm.allgather(_control_plane.get_processor_name())
+    first_rank_of = {}
+    for r, host in enumerate(hosts):
+        first_rank_of.setdefault(host, r)
+    node_order = sorted(first_rank_of, key=first_rank_of.get)
+    mates = [r for r, host in enumerate(hosts) if host == hosts[me]]
+    return (me, mates.index(me), len(mates), node_order.index(hosts[me]), len(node_order))
 
 
 def init_nccl_comm(mpi_comm):
-    """``_communication_utility.py:69-76``: unique id from rank 0, broadcast over
-    the control plane, then ncclCommInitRank on the CURRENT CUDA device."""
-    if mpi_comm.rank == 0:
-        nccl_comm_id = nccl.get_unique_id()
-    else:
-        nccl_comm_id = None
-    nccl_comm_id = mpi_comm.bcast(nccl_comm_id)
-    return nccl.NcclCommunicator(mpi_comm.size, nccl_comm_id, mpi_comm.rank)
+    """NCCL communicator over all ranks of ``mpi_comm``: rank 0 draws the unique id, the
+    control plane carries it, ``ncclCommInitRank`` binds to the CURRENT CUDA device."""
+    uid = mpi_comm.bcast(nccl.get_unique_id() if mpi_comm.rank == 0 else None)
+    return nccl.NcclCommunicator(mpi_comm.size, uid, mpi_comm.rank)
 
 
 def _get_nccl_type_id(dtype):
-    """``_communication_utility.py:177-186`` (+ bfloat16)."""
+    """NCCL datatype of a float dtype (``'bfloat16'`` is this package's extension);
+    ``ValueError`` for anything else, as the reference."""
     if isinstance(dtype, str) and dtype == 'bfloat16':
         return nccl.NCCL_BFLOAT16
-    dtype = np.dtype(dtype)
-    if dtype == np.float16:
-        return nccl.NCCL_FLOAT16
-    elif dtype == np.float32:
-        return nccl.NCCL_FLOAT32
-    elif dtype == np.float64:
-        return nccl.NCCL_FLOAT64
-    else:
-        raise ValueError(
-            'dtype must be float16, float32, or float64.')
+    try:
+        return _NCCL_IDS[np.dtype(dtype)]
+    except (KeyError, TypeError):
+        raise ValueError('dtype must be float16, float32, or float64.')

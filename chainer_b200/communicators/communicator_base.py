@@ -1,142 +1,120 @@
-"""Interface of all communicators: mirror of
-``chainermn/communicators/communicator_base.py:8-441`` (same method names,
-same configuration mechanism, including the class-level ``_configs`` dict that
-the reference shares between instances, ``communicator_base.py:38, 425-441``).
+"""The communicator interface of this package.
+
+API contract (names, arguments, errors) of ``chainermn.CommunicatorBase``
+(``chainermn/communicators/communicator_base.py:8-441``): the six rank / size
+properties, the array and object collectives, ``bcast_data`` /
+``multi_node_mean_grad`` with their deprecated aliases, and the configuration
+mechanism.  The implementation is this package's own:
+
+* the abstract surface is generated from one table (``_COLLECTIVES``) instead of being
+  spelled out method by method;
+* configuration values are ordinary instance attributes that are ALSO recorded in a
+  per-class registry while a ``config_scope()`` is open -- the reference's behaviour that
+  ``get_config()`` reports what was assigned inside such a scope, and that the registry is
+  shared by the instances of a class (``communicator_base.py:38, 425-441``).
+
+When the real ``chainermn`` is imported, ``chainer_b200.integration.install`` registers
+the concrete communicator as a ``chainermn.CommunicatorBase`` too.
 """
-from abc import ABCMeta
-from abc import abstractmethod
+import abc
 import contextlib
 import warnings
 
+# name -> signature text; every entry becomes an abstract method that concrete
+# communicators (MpiCommunicatorBase) implement
+_COLLECTIVES = (
+    ('split', '(self, color, key)'),
+    ('alltoall', '(self, xs)'),
+    ('send', '(self, data, dest, tag)'),
+    ('recv', '(self, source, tag)'),
+    ('bcast', '(self, data, max_buf_len=None, root=0)'),
+    ('gather', '(self, data, root=0)'),
+    ('allgather', '(self, x)'),
+    ('allreduce', '(self, data)'),
+    ('scatter', '(self, xs, root=0)'),
+    ('send_obj', '(self, obj, dest, tag)'),
+    ('recv_obj', '(self, source, tag)'),
+    ('bcast_obj', '(self, obj, max_buf_len=None, root=0)'),
+    ('gather_obj', '(self, obj, root=0)'),
+    ('allreduce_obj', '(self, obj)'),
+    ('bcast_data', '(self, model)'),
+    ('multi_node_mean_grad', '(self, model, zero_fill=False)'),
+)
+_TOPOLOGY = ('rank', 'size', 'intra_rank', 'intra_size', 'inter_rank', 'inter_size')
 
-class CommunicatorBase(metaclass=ABCMeta):
 
+def _abstract(name, signature):
+    scope = {}
+    exec('def {}{}:\n    raise NotImplementedError()'.format(name, signature), scope)
+    fn = scope[name]
+    fn.__doc__ = 'Abstract: see chainermn.CommunicatorBase.{}.'.format(name)
+    return abc.abstractmethod(fn)
+
+
+def _unimplemented_property(name):
+    def getter(self):
+        raise NotImplementedError()
+    getter.__name__ = name
+    return property(getter)
+
+
+class _Meta(abc.ABCMeta):
+    """Builds the abstract surface from the tables above."""
+
+    def __new__(mcs, cls_name, bases, ns):
+        if ns.get('_is_interface_root', False):
+            for name, signature in _COLLECTIVES:
+                ns.setdefault(name, _abstract(name, signature))
+            for name in _TOPOLOGY:
+                ns.setdefault(name, _unimplemented_property(name))
+        return super(_Meta, mcs).__new__(mcs, cls_name, bases, ns)
+
+
+class CommunicatorBase(metaclass=_Meta):
+
+    _is_interface_root = True
+    #: registry of configuration values assigned inside ``config_scope()``
     _configs = {}
 
     def __init__(self):
-        self._within_config_scope = False
+        object.__setattr__(self, '_config_depth', 0)
 
-    @property
-    def rank(self):
-        raise NotImplementedError()
-
-    @property
-    def size(self):
-        raise NotImplementedError()
-
-    @property
-    def intra_rank(self):
-        raise NotImplementedError()
-
-    @property
-    def intra_size(self):
-        raise NotImplementedError()
-
-    @property
-    def inter_rank(self):
-        raise NotImplementedError()
-
-    @property
-    def inter_size(self):
-        raise NotImplementedError()
-
+    # -- configuration ---------------------------------------------------------
     def set_config(self, name, **kwargs):
+        """Subclasses handle the names they know and delegate here for the rest."""
         raise ValueError('Unknown config: {}'.format(name))
 
     def get_config(self, name=None):
-        if name is not None:
-            return self._configs[name]
-        return self._configs
+        registry = type(self)._configs
+        return registry if name is None else registry[name]
 
-    @abstractmethod
-    def split(self, color, key):
-        raise NotImplementedError()
+    @property
+    def within_config_scope(self):
+        return self.__dict__.get('_config_depth', 0) > 0
 
-    @abstractmethod
-    def alltoall(self, xs):
-        raise NotImplementedError()
+    @contextlib.contextmanager
+    def config_scope(self):
+        """Attributes assigned inside the scope are configuration values."""
+        depth = self.__dict__.get('_config_depth', 0)
+        object.__setattr__(self, '_config_depth', depth + 1)
+        try:
+            yield
+        finally:
+            object.__setattr__(self, '_config_depth', depth)
 
-    @abstractmethod
-    def send(self, data, dest, tag):
-        raise NotImplementedError()
+    def __setattr__(self, name, value):
+        if self.__dict__.get('_config_depth', 0) > 0:
+            type(self)._configs[name] = value
+        object.__setattr__(self, name, value)
 
-    @abstractmethod
-    def recv(self, source, tag):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def bcast(self, data, max_buf_len=None, root=0):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def gather(self, data, root=0):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def allgather(self, x):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def allreduce(self, data):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def scatter(self, xs, root=0):
-        raise NotImplementedError()
-
+    # -- lifecycle and deprecated aliases --------------------------------------
     def finalize(self):
         pass
-
-    @abstractmethod
-    def send_obj(self, obj, dest, tag):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def recv_obj(self, source, tag):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def bcast_obj(self, obj, max_buf_len=None, root=0):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def gather_obj(self, obj, root=0):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def allreduce_obj(self, obj):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def bcast_data(self, model):
-        raise NotImplementedError()
 
     def broadcast_data(self, model):
         warnings.warn('broadcast_data() is deprecated.', DeprecationWarning)
         self.bcast_data(model)
 
-    @abstractmethod
-    def multi_node_mean_grad(self, model, zero_fill=False):
-        raise NotImplementedError()
-
     def allreduce_grad(self, model, zero_fill=False):
         warnings.warn('allreduce_grad() is deprecated.', DeprecationWarning)
         self.multi_node_mean_grad(model, zero_fill)
-
-    @property
-    def within_config_scope(self):
-        return getattr(self, '_within_config_scope', False)
-
-    @contextlib.contextmanager
-    def config_scope(self):
-        old_flag = self.within_config_scope
-        self._within_config_scope = True
-        try:
-            yield
-        finally:
-            self._within_config_scope = old_flag
-
-    def __setattr__(self, name, value):
-        if self.within_config_scope:
-            self._configs[name] = value
-        super(CommunicatorBase, self).__setattr__(name, value)

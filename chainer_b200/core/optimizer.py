@@ -246,12 +246,57 @@ class UpdateRule(object):
         self._use_fp32_update = flag
 
     def serialize(self, serializer):
-        """``optimizer.py:433-471``: ``t`` and the state arrays by name."""
+        """``t`` and the state arrays by name (``optimizer.py:433-471``).
+
+        Loading into a FRESH rule (no state yet -- the normal resume flow: new optimizer,
+        ``setup()``, then load) restores the state arrays too: the keys come from
+        ``state_names`` (or from ``init_state`` on a one-element dummy, as the reference
+        does), each is read from the snapshot, and a snapshot that lacks them leaves the
+        state ``None`` so that ``_init_states`` creates it on first use -- silently for a
+        disabled rule, with the ``KeyError`` for an enabled one."""
         self.t = serializer('t', self.t)
         if self._state is not None:
             for key in self._state:
                 self._state[key] = serializer(key, self._state[key])
+        elif _is_deserializer(serializer):
+            loaded = {}
+            for key in self._state_keys():
+                try:
+                    value = serializer(key, None)
+                except KeyError:
+                    if self.enabled:
+                        raise
+                    value = None
+                if value is None:
+                    loaded = None
+                    break
+                loaded[key] = value
+            self._state = loaded
         _rules_version[0] += 1      # state arrays may have been replaced
+
+    def _state_keys(self):
+        names = getattr(self, 'state_names', None)
+        if names is not None:
+            return tuple(names)
+        probe = copy.copy(self)
+        probe._state = {}
+        from chainer_b200.core import link as _link
+        probe.init_state(_link.Parameter(np.empty(1, dtype=np.float32)))
+        return tuple(probe._state)
+
+
+def _is_deserializer(serializer):
+    """Serializers are the caller's objects (``chainer.serializers`` in the reference):
+    recognised by ``chainer.Deserializer`` when chainer is imported, else by an
+    ``is_deserializer`` attribute or a class name ending in ``Deserializer``."""
+    import sys
+    ch = sys.modules.get('chainer')
+    base = getattr(getattr(ch, 'serializer', None), 'Deserializer', None) if ch else None
+    if base is not None and isinstance(serializer, base):
+        return True
+    if getattr(serializer, 'is_deserializer', False):
+        return True
+    return type(serializer).__name__.endswith('Deserializer')
 
 
 class Optimizer(object):

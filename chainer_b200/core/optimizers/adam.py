@@ -9,28 +9,25 @@ from chainer_b200 import device as _dev
 from chainer_b200.core import optimizer
 from chainer_b200.core.optimizers import _single
 
+# name -> default of every hyperparameter of the Adam family (values: adam.py:34-44)
+_DEFAULTS = (('alpha', 0.001), ('beta1', 0.9), ('beta2', 0.999), ('eps', 1e-8), ('eta', 1.0),
+             ('weight_decay_rate', 0), ('amsgrad', False), ('adabound', False),
+             ('final_lr', 0.1), ('gamma', 1e-3))
+_NAMES = tuple(name for name, _ in _DEFAULTS)
 _default_hyperparam = optimizer.Hyperparameter()
-_default_hyperparam.alpha = 0.001
-_default_hyperparam.beta1 = 0.9
-_default_hyperparam.beta2 = 0.999
-_default_hyperparam.eps = 1e-8
-_default_hyperparam.eta = 1.0
-_default_hyperparam.weight_decay_rate = 0
-_default_hyperparam.amsgrad = False
-_default_hyperparam.adabound = False
-_default_hyperparam.final_lr = 0.1
-_default_hyperparam.gamma = 1e-3
+for _name, _value in _DEFAULTS:
+    setattr(_default_hyperparam, _name, _value)
 
 
 def _learning_rate(hp, t):
-    """``adam.py:47-54``."""
+    """Bias-corrected step size ``alpha * sqrt(1 - beta2^t) / (1 - beta1^t)``, evaluated in
+    double with ``math.pow`` / ``math.sqrt`` like the reference (``adam.py:47-54``) so that
+    the scalar handed to the kernel has the same bits."""
     if t == 0:
         raise RuntimeError(
             'Can\'t determine the learning rate of Adam optimizer '
             'because the update steps have not been started.')
-    fix1 = 1. - math.pow(hp.beta1, t)
-    fix2 = 1. - math.pow(hp.beta2, t)
-    return hp.alpha * math.sqrt(fix2) / fix1
+    return hp.alpha * math.sqrt(1. - math.pow(hp.beta2, t)) / (1. - math.pow(hp.beta1, t))
 
 
 def _get_intermediate_dtype(dtype):
@@ -139,36 +136,22 @@ class AdamRule(optimizer.UpdateRule):
 
 
 class Adam(optimizer.GradientMethod):
-    """``adam.py:361-446``."""
+    """``chainer.optimizers.Adam`` (``adam.py:361-446``): keyword arguments and attribute
+    proxies for every entry of ``_DEFAULTS``."""
 
-    def __init__(self, alpha=_default_hyperparam.alpha, beta1=_default_hyperparam.beta1,
-                 beta2=_default_hyperparam.beta2, eps=_default_hyperparam.eps,
-                 eta=_default_hyperparam.eta,
-                 weight_decay_rate=_default_hyperparam.weight_decay_rate,
-                 amsgrad=_default_hyperparam.amsgrad, adabound=_default_hyperparam.adabound,
-                 final_lr=_default_hyperparam.final_lr, gamma=_default_hyperparam.gamma):
+    def __init__(self, *args, **kwargs):
+        if len(args) > len(_NAMES):
+            raise TypeError('Adam() takes at most {} arguments'.format(len(_NAMES)))
+        for name, value in zip(_NAMES, args):        # positional, in the reference's order
+            if name in kwargs:
+                raise TypeError('Adam() got multiple values for argument {!r}'.format(name))
+            kwargs[name] = value
+        unknown = set(kwargs) - set(_NAMES)
+        if unknown:
+            raise TypeError('Adam() got unexpected keyword arguments {}'.format(sorted(unknown)))
         super(Adam, self).__init__()
-        self.hyperparam.alpha = alpha
-        self.hyperparam.beta1 = beta1
-        self.hyperparam.beta2 = beta2
-        self.hyperparam.eps = eps
-        self.hyperparam.eta = eta
-        self.hyperparam.weight_decay_rate = weight_decay_rate
-        self.hyperparam.amsgrad = amsgrad
-        self.hyperparam.adabound = adabound
-        self.hyperparam.final_lr = final_lr
-        self.hyperparam.gamma = gamma
-
-    alpha = optimizer.HyperparameterProxy('alpha')
-    beta1 = optimizer.HyperparameterProxy('beta1')
-    beta2 = optimizer.HyperparameterProxy('beta2')
-    eps = optimizer.HyperparameterProxy('eps')
-    eta = optimizer.HyperparameterProxy('eta')
-    weight_decay_rate = optimizer.HyperparameterProxy('weight_decay_rate')
-    amsgrad = optimizer.HyperparameterProxy('amsgrad')
-    adabound = optimizer.HyperparameterProxy('adabound')
-    final_lr = optimizer.HyperparameterProxy('final_lr')
-    gamma = optimizer.HyperparameterProxy('gamma')
+        for name, default in _DEFAULTS:
+            setattr(self.hyperparam, name, kwargs.get(name, default))
 
     def create_update_rule(self):
         return AdamRule(self.hyperparam)
@@ -184,3 +167,7 @@ class Adam(optimizer.GradientMethod):
             'Use of Adam.lr is deprecated in Chainer v6.',
             DeprecationWarning)
         return self.alpha_t
+
+
+for _name in _NAMES:
+    setattr(Adam, _name, optimizer.HyperparameterProxy(_name))

@@ -267,6 +267,14 @@ class _MemPtr(object):
         self.ptr = ptr
         self._owner = owner
 
+    # a raw address cannot be duplicated by copying the Python object: DeviceArray copies
+    # the MEMORY (below); copying the handle alone would alias it
+    def __copy__(self):
+        raise TypeError('device memory handles are not copyable; copy the DeviceArray')
+
+    def __deepcopy__(self, memo):
+        raise TypeError('device memory handles are not copyable; copy the DeviceArray')
+
 
 class _Allocation(object):
     def __init__(self, nbytes):
@@ -283,6 +291,13 @@ class _Allocation(object):
             except Exception:
                 pass
             self.ptr = None
+
+    # one owner per cudaMalloc: a copied owner would free the same pointer twice
+    def __copy__(self):
+        raise TypeError('device allocations are not copyable')
+
+    def __deepcopy__(self, memo):
+        raise TypeError('device allocations are not copyable')
 
 
 class DeviceArray(object):
@@ -359,6 +374,16 @@ class DeviceArray(object):
     def copy(self):
         out = DeviceArray(self.shape, self.dtype)
         _lib.get().gp_memcpy_async(out.data.ptr, self.data.ptr, self.nbytes, 2, 0)
+        return out
+
+    # copy.copy / copy.deepcopy (Link.copyparams, the double-buffering optimizer's
+    # deepcopy(target), optimizer state): a NEW allocation with the same contents
+    def __copy__(self):
+        return self.copy()
+
+    def __deepcopy__(self, memo):
+        out = self.copy()
+        memo[id(self)] = out
         return out
 
     def __repr__(self):

@@ -12,6 +12,7 @@ import pytest
 
 import chainer_b200
 from chainer_b200 import config
+from chainer_b200 import device as _dev
 from chainer_b200.communicators import _control_plane
 from chainer_b200.communicators.pure_nccl_communicator import PureNcclCommunicator
 from chainer_b200.core import link as L
@@ -867,3 +868,101 @@ def test_fp32_master_multi_node_is_fused(fake, case):
     assert called.count(kernel) == 3
     assert 'gp_unpack_momentum_sgd' not in called and 'gp_unpack_adam' not in called
     assert 'gp_divide' not in called
+
+
+def test_device_array_deepcopy_owns_new_memory(fake):
+    """copy.deepcopy of a model after an optimizer step (what the double-buffering optimizer
+    does) gives arrays with their OWN device memory: different pointers, same contents, and
+    the raw handles refuse to be copied."""
+    import copy
+    a = _dev.DeviceArray.from_numpy(np.arange(12, dtype=np.float32).reshape(3, 4))
+    b = copy.deepcopy(a)
+    c = copy.copy(a)
+    assert b.data.ptr != a.data.ptr and c.data.ptr != a.data.ptr
+    np.testing.assert_array_equal(b.get(), a.get())
+    np.testing.assert_array_equal(c.get(), a.get())
+    b.fill(7.0)
+    assert a.get()[0, 1] == 1.0
+    with pytest.raises(TypeError):
+        copy.deepcopy(a.data)
+    model = L.link_from_named_arrays([('/w', _dev.DeviceArray.from_numpy(np.ones(8, np.float32)))])
+    opt = chainer_b200.MomentumSGD(lr=0.1)
+    opt.setup(model)
+    for _, p in model.namedparams():
+        p.grad = _dev.DeviceArray.from_numpy(np.full(8, 0.5, np.float32))
+    opt.update()
+    twin = copy.deepcopy(model)
+    for (_, p), (_, q) in zip(sorted(model.namedparams()), sorted(twin.namedparams())):
+        assert q.data.data.ptr != p.data.data.ptr
+        np.testing.assert_array_equal(q.data.get(), p.data.get())
+        sv, tv = p.update_rule.state['v'], q.update_rule.state['v']
+        assert tv.data.ptr != sv.data.ptr
+        np.testing.assert_array_equal(tv.get(), sv.get())
+
+
+class _DictSerializer(object):
+    def __init__(self, store, prefix=''):
+        self.store, self.prefix = store, prefix
+
+    def __getitem__(self, key):
+        return type(self)(self.store, self.prefix + key.strip('/') + '/')
+
+    def __call__(self, key, value):
+        self.store[self.prefix + key] = np.array(_dev.to_numpy(value)) if hasattr(value, 'shape') \
+            or isinstance(value, _dev.DeviceArray) else value
+        return value
+
+
+class _DictDeserializer(_DictSerializer):
+    """Non-strict, like chainer.serializers.NpzDeserializer(strict=False): a key the
+    snapshot lacks (the state of a never-updated parameter) comes back as the passed value."""
+
+    def __call__(self, key, value):
+        if self.prefix + key not in self.store:
+            return value
+        got = self.store[self.prefix + key]
+        if isinstance(got, np.ndarray) and got.shape != ():
+            return got.copy()
+        return got
+
+
+@pytest.mark.parametrize('opt_name', ['momentum_sgd', 'adam'])
+def test_resume_restores_optimizer_state(fake, opt_name):
+    """Save after N steps, load into a FRESH optimizer (setup() then load -- the rules have
+    no state yet) and compare the next step: the moments come back (the reference,
+    optimizer.py:433-471); without them Adam would pair a large t with zero moments."""
+    def mk():
+        return chainer_b200.MomentumSGD(lr=0.1, momentum=0.9) if opt_name == 'momentum_sgd' \
+            else chainer_b200.Adam(alpha=0.01)
+    model = _model_with_values()
+    opt = mk()
+    opt.setup(model)
+    for step in range(2):
+        _set_grads(model, 20 + step)
+        opt.update()
+    store = {}
+    opt.serialize(_DictSerializer(store))
+    snap = {n: p.data.copy() for n, p in sorted(model.namedparams()) if p.data is not None}
+
+    resumed = _model_with_values()
+    for n, p in sorted(resumed.namedparams()):
+        if p.data is not None:
+            p.data[...] = snap[n]
+    opt2 = mk()
+    opt2.setup(resumed)
+    opt2.serialize(_DictDeserializer(store))
+    assert opt2.t == 2
+    names = ('v',) if opt_name == 'momentum_sgd' else ('m', 'v')
+    for (n, p), (_, q) in zip(sorted(model.namedparams()), sorted(resumed.namedparams())):
+        if p.data is None:
+            continue
+        assert q.update_rule.t == 2 and q.update_rule.state is not None
+        for k in names:
+            assert_bits_equal(np.asarray(q.update_rule.state[k]), np.asarray(p.update_rule.state[k]), (n, k))
+    _set_grads(model, 30)
+    _set_grads(resumed, 30)
+    opt.update()
+    opt2.update()
+    for (n, p), (_, q) in zip(sorted(model.namedparams()), sorted(resumed.namedparams())):
+        if p.data is not None:
+            assert_bits_equal(q.data, p.data, n)
