@@ -184,6 +184,8 @@ PROTOTYPES = {
     'gp_p2p_set_small': (c_int, [c_void_p, _P(c_void_p), _P(c_void_p), c_int64]),
     'gp_p2p_allreduce_small': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,
                                        c_void_p]),
+    'gp_nvtx_push': (c_int, [c_char_p]),
+    'gp_nvtx_pop': (c_int, []),
     'gp_set_tuning': (c_int, [c_char_p, c_int]),
     'gp_get_tuning': (c_int, [c_char_p, _P(c_int)]),
 }
@@ -199,7 +201,7 @@ KERNEL_FUNCS = frozenset([
     'gp_unpack_momentum_sgd_master', 'gp_unpack_adam_master'])
 
 # functions whose int return value is an error code
-_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',
+_NO_CHECK = {'gp_last_error', 'gp_abi_version', 'gp_nvtx_push', 'gp_nvtx_pop', 'gp_bn_workspace_bytes', 'gp_p2p_flag_bytes', 'gp_p2p_small_bytes',
              'gp_sqnorm_workspace_bytes', 'gp_step_supported', 'gp_step_words_bytes', 'gp_step_tile_elems'}
 
 
@@ -297,6 +299,25 @@ def set_backend_for_testing(obj):
     prev = _lib
     _lib = obj
     return prev
+
+
+class nvtx_range(object):
+    """``with nvtx_range('pack'):`` -- an NVTX range around the enclosed launches when
+    CHAINER_B200_NVTX=1 (a no-op context otherwise, and without a profiler attached)."""
+    enabled = os.environ.get('CHAINER_B200_NVTX', '0') not in ('0', '', 'false', 'False')
+
+    def __init__(self, name):
+        self.name = name.encode() if isinstance(name, str) else name
+
+    def __enter__(self):
+        if nvtx_range.enabled:
+            get().gp_nvtx_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if nvtx_range.enabled:
+            get().gp_nvtx_pop()
+        return False
 
 
 def find_libnccl():

@@ -339,15 +339,18 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             self._check_ready_to_allreduce_meta(n, dtype)
         bounds = self._bucket_bounds(n, itemsize)
         nb = len(bounds) - 1
+        nv = _lib.nvtx_range
         if self.size == 1:
-            _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+            with nv('gradpath.pack'):
+                _memory_utility._batched_pack_params(pd, buf, dtype, stream)
             # a one-rank SUM is the identity: nothing to launch (the reference
             # would copy A to B here)
             self.nccl_comm.allReduce(buf.ptr(), buf.ptr(), n, type_id, nccl.NCCL_SUM,
                                      stream.ptr)
             if debug:
                 self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
-            consume(0, n)
+            with nv('gradpath.update'):
+                consume(0, n)
             return
         reduce_range = None
         if self._mc_active(buf):
@@ -370,11 +373,14 @@ class PureNcclCommunicator(mpi_communicator_base.MpiCommunicatorBase):
             # stream under the HBM-bound pack of chunk i+1 and update of chunk i-1.
             cb = self._chunk_bounds(n, itemsize, chunk_bytes)
             if len(cb) == 2:
-                _memory_utility._batched_pack_params(pd, buf, dtype, stream)
-                reduce_range(dtype, 0, n, stream)
+                with nv('gradpath.pack'):
+                    _memory_utility._batched_pack_params(pd, buf, dtype, stream)
+                with nv('gradpath.allreduce'):
+                    reduce_range(dtype, 0, n, stream)
                 if debug:
                     self._ensure_all_finite_device(buf.ptr(), dtype, n, stream)
-                consume(0, n)
+                with nv('gradpath.update'):
+                    consume(0, n)
                 return
             if self._comm_stream is None:
                 self._comm_stream = _dev.Stream(non_blocking=True)
@@ -850,13 +856,14 @@ class _FusedPlan(object):
             p2p.step_prepare(n_elems)
             handle = p2p.handle
         sp = stream.ptr
-        if key[0] == 'momentum_sgd':
-            lib.gp_step_momentum_sgd(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs,
-                                     t.n_params, n_elems, scale, key[1], key[2], wg, hint, sp)
-        else:
-            lib.gp_step_adam(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs, t.n_params,
-                             n_elems, scale, key[1], key[2], key[3], key[4], key[5], key[6],
-                             key[7], key[8], key[9], wg, hint, sp)
+        with _lib.nvtx_range('gradpath.step (pack + allreduce + update, one launch)'):
+            if key[0] == 'momentum_sgd':
+                lib.gp_step_momentum_sgd(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs,
+                                         t.n_params, n_elems, scale, key[1], key[2], wg, hint, sp)
+            else:
+                lib.gp_step_adam(handle, mc_ptr, buf.ptr(), buf_id, t.d_csum, t.d_segs,
+                                 t.n_params, n_elems, scale, key[1], key[2], key[3], key[4],
+                                 key[5], key[6], key[7], key[8], key[9], wg, hint, sp)
         return True
 
 

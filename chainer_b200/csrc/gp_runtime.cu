@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gp_bulk.cuh"
 
 static thread_local char g_err[512] = "";
@@ -98,6 +100,13 @@ int gp_get_tuning(const char* key, int* value) {
   }
   return 0;
 }
+
+// ------------------------------------------------------------ NVTX ---------
+// Named ranges around the stages of a step (pack / allreduce / update, BN statistics) for
+// Nsight Systems / ncu --nvtx; header-only NVTX v3: no link dependency, a no-op unless a
+// tool is attached.  Reference analogue: chainer/function_hooks/cuda_profile.py:14-24.
+int gp_nvtx_push(const char* name) { return nvtxRangePushA(name ? name : "gradpath"); }
+int gp_nvtx_pop(void) { return nvtxRangePop(); }
 
 // ------------------------------------------------------------ device ------
 int gp_device_count(int* count) { GP_CUDA(cudaGetDeviceCount(count)); return 0; }

@@ -122,9 +122,10 @@ class _NcclImpl(object):
         if p2p is not None:
             # statistics + allReduce + div_by_size + var in ONE kernel: the CTA that finishes
             # the last channel exchanges the 2C values over NVLink peer memory
-            lib.gp_bn_fwd_stats_allreduce(p2p.handle, _dev.device_ptr(x),
-                                          _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
-                                          _dev.device_ptr(buf), _workspace(self.comm, C), 0)
+            with _lib.nvtx_range('mnbn.fwd_stats+allreduce'):
+                lib.gp_bn_fwd_stats_allreduce(p2p.handle, _dev.device_ptr(x),
+                                              _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                                              _dev.device_ptr(buf), _workspace(self.comm, C), 0)
             return _halves(buf, C)
         lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)

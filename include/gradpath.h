@@ -506,6 +506,13 @@ int gp_step_set_tuning(const char* key, int value);
 
 /* key: "threads", "unroll", "ctas_per_sm", "persistent".  For benchmarking
  * sweeps; defaults are the tuned values recorded in DESIGN.md. */
+/* NVTX ranges (Nsight Systems / `ncu --nvtx`): push returns the nesting level or a negative
+ * value when no tool is attached.  The Python layer brackets pack / allreduce / update and
+ * the BN statistics with them when CHAINER_B200_NVTX=1
+ * (reference analogue: chainer/function_hooks/cuda_profile.py:14-24). */
+int gp_nvtx_push(const char* name);
+int gp_nvtx_pop(void);
+
 int gp_set_tuning(const char* key, int value);
 int gp_get_tuning(const char* key, int* value);
 

@@ -69,6 +69,14 @@ class FakeLib(object):
     def gp_last_error(self):
         return b''
 
+    def gp_nvtx_push(self, name):
+        self.calls.append(('nvtx_push', (name,)))
+        return 0
+
+    def gp_nvtx_pop(self):
+        self.calls.append(('nvtx_pop', ()))
+        return 0
+
     def gp_set_tuning(self, key, value):
         self.tuning[key] = value
         return 0
