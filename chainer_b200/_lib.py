@@ -292,9 +292,14 @@ def get():
 
 
 def set_backend_for_testing(obj):
-    """Replace the loaded library by `obj` (tests only: lets the host logic be
-    exercised on machines without a GPU against an oracle-backed double that
-    lives under tests/).  Returns the previous backend."""
+    """Replace the loaded library by `obj` (TESTS ONLY: lets the host logic be exercised on
+    machines without a GPU against an oracle-backed double that lives under tests/).
+    Returns the previous backend.  Refused unless the process is a pytest run or sets
+    CHAINER_B200_TEST_BACKEND=1 explicitly: a product process can never end up on a double."""
+    import sys
+    if 'pytest' not in sys.modules and os.environ.get('CHAINER_B200_TEST_BACKEND') != '1':
+        raise RuntimeError('set_backend_for_testing is test machinery: run under pytest or set '
+                           'CHAINER_B200_TEST_BACKEND=1')
     global _lib
     prev = _lib
     _lib = obj

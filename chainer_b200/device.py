@@ -16,6 +16,7 @@ has swapped in its host-memory double of the C library (``_lib.set_backend_for_t
 """
 import ctypes
 import operator
+import sys as _sys
 
 import numpy as np
 
@@ -38,30 +39,50 @@ def _torch():
         return None
 
 
+_TT = [None, None, None]      # torch.Tensor, {torch dtype: numpy dtype | 'bfloat16'}, {torch dtype: id}
+
+
+def _torch_tables():
+    torch = _torch()
+    if torch is None:
+        return None
+    _TT[0] = torch.Tensor
+    _TT[1] = {torch.float32: np.dtype(np.float32), torch.float16: np.dtype(np.float16),
+              torch.float64: np.dtype(np.float64), torch.bfloat16: BF16,
+              torch.int32: np.dtype(np.int32), torch.int64: np.dtype(np.int64)}
+    _TT[2] = {torch.float32: _lib.GP_F32, torch.float16: _lib.GP_F16,
+              torch.float64: _lib.GP_F64, torch.bfloat16: _lib.GP_BF16}
+    return _TT[0]
+
+
 def is_torch(a):
-    return hasattr(a, 'data_ptr') and hasattr(a, 'numel')
+    t = _TT[0]
+    if t is None:
+        if 'torch' not in _sys.modules:        # nobody can hold a tensor yet
+            return False
+        t = _torch_tables()
+    return t is not None and isinstance(a, t)
 
 
 def array_dtype(a):
     """numpy dtype of an array of any supported module; the string 'bfloat16'
     for torch.bfloat16 (NumPy has no such dtype)."""
     if is_torch(a):
-        torch = _torch()
-        dt = a.dtype
-        if dt == torch.float32:
-            return np.dtype(np.float32)
-        if dt == torch.float16:
-            return np.dtype(np.float16)
-        if dt == torch.float64:
-            return np.dtype(np.float64)
-        if dt == torch.bfloat16:
-            return BF16
-        if dt == torch.int32:
-            return np.dtype(np.int32)
-        if dt == torch.int64:
-            return np.dtype(np.int64)
-        raise ValueError('unsupported torch dtype {}'.format(dt))
+        try:
+            return _TT[1][a.dtype]
+        except KeyError:
+            raise ValueError('unsupported torch dtype {}'.format(a.dtype))
     return np.dtype(a.dtype)
+
+
+def array_dtype_id(a):
+    """``dtype_id(array_dtype(a))`` in one step (the hot callers' form)."""
+    if is_torch(a):
+        try:
+            return _TT[2][a.dtype]
+        except KeyError:
+            raise ValueError('dtype must be float16, float32, or float64.')
+    return dtype_id(np.dtype(a.dtype))
 
 
 def array_size(a):

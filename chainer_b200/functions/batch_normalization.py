@@ -114,7 +114,7 @@ class _NcclImpl(object):
         buf = _new_like(gamma, 2 * C, gdt)
         if self.comm.size == 1:
             # one rank: mean and var straight from the statistics kernel (one launch)
-            lib.gp_bn_fwd_mean_var(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C,
+            lib.gp_bn_fwd_mean_var(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C,
                                    HW, _dev.device_ptr(buf), _dev.dtype_id(gdt),
                                    _workspace(self.comm, C), 0)
             return _halves(buf, C)
@@ -124,10 +124,10 @@ class _NcclImpl(object):
             # the last channel exchanges the 2C values over NVLink peer memory
             with _lib.nvtx_range('mnbn.fwd_stats+allreduce'):
                 lib.gp_bn_fwd_stats_allreduce(p2p.handle, _dev.device_ptr(x),
-                                              _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+                                              _dev.array_dtype_id(x), N, C, HW,
                                               _dev.device_ptr(buf), _workspace(self.comm, C), 0)
             return _halves(buf, C)
-        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
         _allreduce_in_place(self.comm, buf, 2 * C, gdt)
         mean, var = _halves(buf, C)
@@ -142,8 +142,8 @@ class _NcclImpl(object):
         N, HW = _check_layout(axis, gy, C)
         gdt = _dev.array_dtype(gamma)
         buf = _new_like(gamma, 2 * C, gdt)
-        lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.dtype_id(_dev.array_dtype(gy)),
-                            _dev.device_ptr(x_hat), _dev.dtype_id(_dev.array_dtype(x_hat)),
+        lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.array_dtype_id(gy),
+                            _dev.device_ptr(x_hat), _dev.array_dtype_id(x_hat),
                             None, None, _lib.GP_F32, N, C, HW, _dev.device_ptr(buf),
                             _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
         buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
@@ -175,17 +175,17 @@ class _NcclImpl(object):
         if p2p is not None:
             # statistics + allReduce + div_by_size in ONE kernel (see get_mean_and_var)
             lib.gp_bn_bwd_stats_allreduce(p2p.handle, _dev.device_ptr(gy),
-                                          _dev.dtype_id(_dev.array_dtype(gy)), _dev.device_ptr(x),
-                                          _dev.dtype_id(_dev.array_dtype(x)), _dev.device_ptr(mean),
+                                          _dev.array_dtype_id(gy), _dev.device_ptr(x),
+                                          _dev.array_dtype_id(x), _dev.device_ptr(mean),
                                           _dev.device_ptr(inv_std),
-                                          _dev.dtype_id(_dev.array_dtype(mean)), N, C, HW,
+                                          _dev.array_dtype_id(mean), N, C, HW,
                                           _dev.device_ptr(buf), _workspace(self.comm, C), 0)
             gbeta, ggamma = _halves(buf, C)
             return gbeta, ggamma
-        lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.dtype_id(_dev.array_dtype(gy)),
-                            _dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)),
+        lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.array_dtype_id(gy),
+                            _dev.device_ptr(x), _dev.array_dtype_id(x),
                             _dev.device_ptr(mean), _dev.device_ptr(inv_std),
-                            _dev.dtype_id(_dev.array_dtype(mean)), N, C, HW,
+                            _dev.array_dtype_id(mean), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt),
                             _workspace(self.comm, C), 0)
         buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
@@ -208,7 +208,7 @@ class _MpiImpl(object):
         N, HW = _check_layout(axis, x, C)
         gdt = _dev.array_dtype(gamma)
         tmp = _new_like(gamma, 2 * C, gdt)
-        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+        lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
                             _dev.device_ptr(tmp), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
         _dev.Stream.null.synchronize()
         self.comm._multi_node_mean(None, tmp)
@@ -298,7 +298,7 @@ def fwd_apply(x, mean, var, gamma, beta, eps, running_mean=None, running_var=Non
     y = _dev.empty_like(x)
     inv_std = _new_like(gamma, C, sdt)
     rdt = _dev.array_dtype(running_mean) if running_mean is not None else sdt
-    lib.gp_bn_fwd_apply(_dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+    lib.gp_bn_fwd_apply(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
                         _dev.device_ptr(mean), _dev.device_ptr(var), _dev.device_ptr(gamma),
                         _dev.device_ptr(beta), _dev.dtype_id(sdt), float(eps), _dev.device_ptr(y),
                         _dev.device_ptr(inv_std),
@@ -317,8 +317,8 @@ def bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta):
     sdt = _dev.array_dtype(gamma)
     gx = _dev.empty_like(x)
     inv_m = float(np.dtype(sdt).type(1.0 / (N * HW))) if not isinstance(sdt, str) else 1.0 / (N * HW)
-    lib.gp_bn_bwd_apply(_dev.device_ptr(gy), _dev.dtype_id(_dev.array_dtype(gy)),
-                        _dev.device_ptr(x), _dev.dtype_id(_dev.array_dtype(x)), N, C, HW,
+    lib.gp_bn_bwd_apply(_dev.device_ptr(gy), _dev.array_dtype_id(gy),
+                        _dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
                         _dev.device_ptr(mean), _dev.device_ptr(inv_std), _dev.device_ptr(gamma),
                         _dev.device_ptr(ggamma), _dev.device_ptr(gbeta), _dev.dtype_id(sdt),
                         inv_m, _dev.device_ptr(gx), 0)

@@ -26,6 +26,7 @@ def main():
                     help='total elements (the size histogram of ResNet-50 scaled down; host cost '
                          'does not depend on it)')
     args = ap.parse_args()
+    os.environ['CHAINER_B200_TEST_BACKEND'] = '1'     # this tool measures the host path on a double
     import chainer_b200
     from chainer_b200 import _lib, workloads
     from chainer_b200.core.link import link_from_named_arrays
