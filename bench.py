@@ -71,8 +71,9 @@ def parse_args():
     ap.add_argument('--p2p-ctas', type=int, default=None)
     ap.add_argument('--step-tuning', default='',
                     help='comma-separated key=value pairs for gp_step_set_tuning')
-    ap.add_argument('--mnbn', action='store_true',
-                    help='add the MultiNodeBatchNormalization statistics leg (BASELINE configs[2])')
+    ap.add_argument('--no-config3', action='store_true',
+                    help='skip the BASELINE configs[2] legs of the default workload (float16 packed '
+                         'buffer; MultiNodeBatchNormalization statistics)')
     ap.add_argument('--cpu-seconds', type=float, default=10.0,
                     help='budget of the CPU baseline sample')
     ap.add_argument('--parity-steps', type=int, default=3)
@@ -549,10 +550,18 @@ def b200_main(args):
             e2e = {'value': None, 'unit': 'GB/s', 'h2d_bytes_per_step': n * 4,
                    'd2h_bytes_per_step': n * 4, 'error': '%s: %s' % (type(e).__name__, e)}
 
-    # ---- MNBN statistics (BASELINE configs[2]) ----------------------------------
-    mnbn = None
-    if args.mnbn:
-        mnbn = time_mnbn(torch, dist, world, comm, lib)
+    # ---- BASELINE configs[2]: float16 packed buffer + MNBN statistics -------------
+    mnbn = fp16 = None
+    if not args.no_config3 and args.workload == 'resnet50' and args.allreduce_dtype == 'float32':
+        try:
+            fp16 = time_fp16_buffer(torch, dist, world, comm, step, n, optimizer_name, write_grad,
+                                    steps=min(K, 50))
+        except Exception as e:      # noqa: BLE001
+            fp16 = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            mnbn = time_mnbn(torch, dist, world, comm, lib)
+        except Exception as e:      # noqa: BLE001
+            mnbn = {'error': '%s: %s' % (type(e).__name__, e)}
 
     # ---- the img/s half of the metric -------------------------------------------
     train = None
@@ -640,8 +649,11 @@ def b200_main(args):
         line['train'] = train
         if 'img_per_s' in train:
             line['img_per_s'] = train['img_per_s']
-    if mnbn is not None:
-        line['mnbn'] = mnbn
+    if fp16 is not None or mnbn is not None:
+        line['config3'] = {'what': 'BASELINE configs[2]: the same ResNet-50 step with '
+                                   'allreduce_grad_dtype=float16 (fused cast) and the '
+                                   'MultiNodeBatchNormalization statistics of one step',
+                           'float16_buffer': fp16, 'mnbn': mnbn}
     if bus is not None:
         # the step moves S(N+1)/N (multicast) or 2S(N-1)/N (peer memory) bytes per NVLink
         # direction; implied wire rate if the whole step were the exchange
@@ -1080,6 +1092,37 @@ def time_train(torch, dist, rank, world, comm, args, batch=32, steps=12, warmup=
         out.update(leg(False, ''))
         out['fwd_bwd'] = 'eager (host-bound)'
     return out
+
+
+def time_fp16_buffer(torch, dist, world, comm, step, n, optimizer_name, write_grad, steps):
+    """The default workload with `allreduce_grad_dtype=float16` (the packed buffer and the
+    exchange in half precision, cast fused into pack / update) on the same communicator."""
+    comm.set_config('allreduce_grad_dtype', np.float16)
+    try:
+        for k in range(5):
+            step(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            step(k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+    finally:
+        comm.set_config('allreduce_grad_dtype', np.float32)
+        step(0)                       # back on the float32 buffer before the later legs
+        torch.cuda.synchronize()
+    pack_b, upd_b = bytes_per_elem(optimizer_name, 2, write_grad)
+    return {'ms_per_step': ms, 'steps': steps, 'bytes_per_elem': pack_b + upd_b,
+            'value': world * n * (pack_b + upd_b) / (ms * 1e-3) / 1e9, 'unit': 'GB/s',
+            'packed_bytes': n * 2}
 
 
 def time_mnbn(torch, dist, world, comm, lib, batch=32):

@@ -18,12 +18,12 @@
 // (PackUpd below): the packed buffer is written once and never read back.
 //
 // N ranks (2, 4, 8 on one NVSwitch box): tile t is OWNED by rank t % N.
-//   worker CTAs   pack their tiles in tile order; after each tile one
-//                 `st.release.sys` of the epoch into the owner's word packed[t][rank];
-//                 then, per tile, wait for the owner's flag[t] and run the fused
+//   worker CTAs   pack quarter-tile items in order; after each item one
+//                 `st.release.sys` of the epoch into the owner's word packed[t][rank][q];
+//                 then, per item, wait for the owner's flag[t] and run the fused
 //                 update on it;
 //   reducer CTAs  (the first `reducers` CTAs) take the rank's own tiles in order:
-//                 wait until packed[t][0..N-1] show that all N ranks have packed it, sum the N
+//                 wait until packed[t][0..N-1][0..3] show that all N ranks have packed it, sum the N
 //                 copies -- `multimem.ld_reduce` + `multimem.st` through the NVSwitch
 //                 (transport MC) or N peer loads added in rank order + N peer stores
 //                 (transport P2P, bit-exact with the oracle) -- then publish
@@ -48,6 +48,10 @@ namespace {
 #include "gp_p2p.cuh"
 
 constexpr int kStepThreads = 256;
+// Workers pack and update in ITEMS of 1 / kSub tile.  Measured (N = 2, profiles/
+// r02_step_sweep_q_n2_*.json): quarter-tile items shorten both ends of the pipeline but pay
+// a system-scope release per item -- 0.373 ms vs 0.227 ms with whole-tile items -- so kSub = 1.
+constexpr int kSub = 1;
 
 struct StepTables {
   const int64_t* csum;
@@ -112,7 +116,7 @@ struct PackUpd {
 
 // ------------------------------------------------------------------- N ranks --
 struct StepPeers {
-  uint32_t* words[kMaxRanks];  // every rank's [packed: tile_cap x kMaxRanks | flag: tile_cap]
+  uint32_t* words[kMaxRanks];  // every rank's [packed: tile_cap x kMaxRanks x kSub | flag: tile_cap]
   void* bufs[kMaxRanks];       // P2P: this process's mappings of the packed buffers
   char* mc_base;               // MC: multicast address of the packed buffer
   int64_t tile_cap;
@@ -294,8 +298,9 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
     const uint32_t* packed = p.words[p.rank];
     constexpr int E = 16 / (int)sizeof(B);
     for (int64_t t = p.rank + (int64_t)blockIdx.x * p.n; t < a.n_tiles; t += (int64_t)p.reducers * p.n) {
-      // thread r waits for rank r's "tile t packed" word
-      if ((int)threadIdx.x < p.n) spin_until(packed + t * kMaxRanks + threadIdx.x, p.epoch, p.timeout_ns);
+      // thread (r, q) waits for rank r's "quarter q of tile t packed" word
+      if ((int)threadIdx.x < p.n * kSub)
+        spin_until(packed + t * (kMaxRanks * kSub) + threadIdx.x, p.epoch, p.timeout_ns);
       __syncthreads();
       const int64_t lo = t * a.tile_elems;
       const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
       __syncthreads();
       // release: cumulative over the CTA's stores (ordered before it by bar.sync)
       if ((int)threadIdx.x < p.n)
-        st_release_sys(p.words[threadIdx.x] + p.tile_cap * kMaxRanks + t, p.epoch);
+        st_release_sys(p.words[threadIdx.x] + p.tile_cap * (kMaxRanks * kSub) + t, p.epoch);
     }
     return;
   }
@@ -313,21 +318,31 @@ __global__ void __launch_bounds__(kStepThreads) stepn_kernel(const StepTables a,
   const int64_t* cs = stage_csum(a, s_csum);
   const int64_t w = (int64_t)blockIdx.x - p.reducers;
   const int64_t nw = (int64_t)gridDim.x - p.reducers;
-  for (int64_t t = w; t < a.n_tiles; t += nw) {
-    const int64_t lo = t * a.tile_elems;
-    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+  const int64_t sub = a.tile_elems / kSub;
+  const int64_t n_items = (a.n_elems + sub - 1) / sub;
+  for (int64_t i = w; i < n_items; i += nw) {
+    const int64_t lo = i * sub;
+    const int64_t hi = lo + sub < a.n_elems ? lo + sub : a.n_elems;
     gpw::walk_range<PackOp, B, 4, 0, GP_F32>(cs, a.segs, a.n_segs, lo, hi, pk);
     __syncthreads();
     // release: cumulative over the CTA's stores (ordered before it by bar.sync)
-    if (threadIdx.x == 0) st_release_sys(p.words[t % p.n] + t * kMaxRanks + p.rank, p.epoch);
+    const int64_t t = i / kSub;
+    if (threadIdx.x == 0)
+      st_release_sys(p.words[t % p.n] + t * (kMaxRanks * kSub) + p.rank * kSub + (i - t * kSub), p.epoch);
   }
-  const uint32_t* flag = p.words[p.rank] + p.tile_cap * kMaxRanks;
-  for (int64_t t = w; t < a.n_tiles; t += nw) {
+  // a short last tile: its missing quarters are signalled as packed too
+  if (w == 0 && threadIdx.x == 0) {
+    const int64_t t = a.n_tiles - 1;
+    for (int64_t q = n_items - t * kSub; q < kSub; ++q)
+      st_release_sys(p.words[t % p.n] + t * (kMaxRanks * kSub) + p.rank * kSub + q, p.epoch);
+  }
+  const uint32_t* flag = p.words[p.rank] + p.tile_cap * (kMaxRanks * kSub);
+  for (int64_t i = w; i < n_items; i += nw) {
     // the acquire also drops this SM's L1 lines of the tile (written by pack earlier)
-    if (threadIdx.x == 0) spin_until(flag + t, p.epoch, p.timeout_ns);
+    if (threadIdx.x == 0) spin_until(flag + i / kSub, p.epoch, p.timeout_ns);
     __syncthreads();
-    const int64_t lo = t * a.tile_elems;
-    const int64_t hi = lo + a.tile_elems < a.n_elems ? lo + a.tile_elems : a.n_elems;
+    const int64_t lo = i * sub;
+    const int64_t hi = lo + sub < a.n_elems ? lo + sub : a.n_elems;
     gpw::walk_range<Upd, B, Upd::kDefaultUnroll, 1, GP_F32>(cs, a.segs, a.n_segs, lo, hi, up);
   }
 }
@@ -340,7 +355,7 @@ struct StepTuning {
   int ctas_per_sm;  // cap of resident CTAs per SM (0: the occupancy)
   int reducers_mc, reducers_p2p;
 };
-StepTuning g_step = {16384, 0, 4, 4, 96, 192};
+StepTuning g_step = {16384, 0, 8, 4, 256, 192};
 
 template <class K>
 int occupancy(K kernel, size_t smem) {
@@ -401,12 +416,15 @@ int launch_stepn_t(const StepTables& a, StepPeers p, size_t smem, const PackOp& 
   int occ = occupancy(kernel, smem);
   if (g_step.ctas_per_sm > 0 && g_step.ctas_per_sm < occ) occ = g_step.ctas_per_sm;
   const int64_t cap = (int64_t)gp_sm_count_cached() * occ;   // everything resident at once
-  int64_t reducers = g_step.reducers > 0 ? g_step.reducers : (p.mc_base ? g_step.reducers_mc : g_step.reducers_p2p);
+  // defaults from the sweeps of tools/step_sweep.py (profiles/r02_step_sweep_n*.json):
+  // multicast 256 / N reducer CTAs (N = 8: 32, N = 4: 64), peer memory 192
+  int64_t reducers = g_step.reducers > 0 ? g_step.reducers
+                                          : (p.mc_base ? g_step.reducers_mc / p.n : g_step.reducers_p2p);
   const int64_t own_tiles = (a.n_tiles + p.n - 1) / p.n;
   if (reducers > own_tiles) reducers = own_tiles;
   if (reducers < 1) reducers = 1;
   if (reducers > cap / 2) reducers = cap / 2 > 0 ? cap / 2 : 1;
-  int64_t workers = a.n_tiles;
+  int64_t workers = a.n_tiles * kSub;
   if (workers > cap - reducers) workers = cap - reducers;
   if (workers < 1) workers = 1;
   p.reducers = (int)reducers;
@@ -511,7 +529,7 @@ int gp_step_supported(int n_ranks, int buf_dtype, int layout_hint, double scale,
 }
 
 size_t gp_step_words_bytes(int64_t tile_cap) {
-  return (size_t)tile_cap * (kMaxRanks + 1) * sizeof(uint32_t);
+  return (size_t)tile_cap * (kMaxRanks * kSub + 1) * sizeof(uint32_t);
 }
 
 int gp_step_tile_elems(void) { return g_step.tile_elems; }

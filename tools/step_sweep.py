@@ -66,7 +66,7 @@ def main():
         opt.update()
     step(0)
     rows = []
-    defaults = dict(tile_elems=16384, reducers=0, unroll=4, ctas_per_sm=4)
+    defaults = dict(tile_elems=16384, reducers=0, unroll=8, ctas_per_sm=4)
     configs = [c for c in args.configs.split(';') if c] or ['']
     for cfg in configs:
         kv = dict(defaults)
