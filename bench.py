@@ -617,15 +617,21 @@ def b200_main(args):
         'step_frac_of_nominal_8TBs': step_bytes / ms_step / 1e6 / NOMINAL_HBM_GBS,
     }
     if dom.startswith('gp_step'):
-        roofline['note'] = (
-            'one launch = the whole step; algorithmic bytes follow SURVEY 8(d) (pack {} + update {} '
-            'B/elem), of which the {} B/elem re-read of the packed buffer is served from L2 (the tile '
-            'was written microseconds earlier by the same kernel), so `achieved` can exceed the DRAM '
-            'peak; expected DRAM traffic {} B/elem'.format(pack_b, upd_b, bsz, pack_b + upd_b - bsz))
-        if world > 1:
-            roofline['note'] += '; at N > 1 the launch also contains the NVLink-bound reduction ' \
-                                '(see `allreduce`), which bounds its duration'
-
+        if world == 1:
+            roofline['note'] = (
+                'one launch = the whole step; algorithmic bytes follow SURVEY 8(d) (pack {} + update '
+                '{} B/elem) although pack and update are fused at the register level: the packed '
+                'buffer is written once and never read back, so the real DRAM traffic is {} B/elem '
+                '(ncu: `traffic`) and `achieved` can exceed the DRAM copy peak; in DRAM bytes the '
+                'launch runs at {:.3f} of the measured peak'.format(
+                    pack_b, upd_b, pack_b + upd_b - bsz,
+                    n * (pack_b + upd_b - bsz) / (dom_us * 1e-6) / 1e9 / peak))
+        else:
+            roofline['note'] = (
+                'one launch = the whole step incl. the NVLink-bound exchange over {} ranks, which '
+                'bounds its duration (see `allreduce`: the stand-alone reduction of the same buffer); '
+                'algorithmic HBM bytes follow SURVEY 8(d) (pack {} + update {} B/elem)'.format(
+                    world, pack_b, upd_b))
     line = {
         'metric': METRIC, 'value': value, 'unit': 'GB/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',

@@ -43,8 +43,9 @@ def test_multi_gpu_path(world_size, transport):
     assert out.returncode == 0, out.stdout[-6000:]
     for r in range(world_size):
         assert 'GPU RANK %d OK' % r in out.stdout
-    for line in out.stdout.splitlines():
-        if line.startswith('MNBN statistics exchange'):
+    for line in out.stdout.splitlines():      # the worker's milestones, for the -rA log
+        if line.startswith(('MNBN statistics exchange', 'ONE-LAUNCH STEP OK', 'MULTICAST',
+                            'GPU RANK')):
             print(line)
     if transport != 'nccl':
         assert 'ONE-LAUNCH STEP OK' in out.stdout

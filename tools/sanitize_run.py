@@ -52,9 +52,10 @@ def main():
     y = bn(x)
     y.backward(torch.randn_like(y))
     torch.cuda.synchronize()
+    transport = 'single rank' if world == 1 else (
+        'multicast' if comm._mc_active(comm.gpu_buffer_a) else 'peer memory')
     comm.finalize()
-    print('SANITIZE RANK %d DONE (transport: %s)' % (rank, 'single' if world == 1 else 'peer'),
-          flush=True)
+    print('SANITIZE RANK %d DONE (transport: %s)' % (rank, transport), flush=True)
 
 
 if __name__ == '__main__':
