@@ -1156,33 +1156,61 @@ def time_mnbn(torch, dist, world, comm, lib, batch=32):
         for _, s in reversed(layers):
             x, gy, gamma, mean, inv_std = uniq[s]
             impl.get_ggamma_and_gbeta_from_x(None, gamma, gy, x, mean, inv_std)
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        t_enq = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        if world > 1:
+            t = torch.tensor([us], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            us = float(t.item())
+        return us, 1e6 * t_enq / reps
     for _ in range(3):
         one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    reps = 10
     c0 = lib.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(reps):
-        one_step()
-    e1.record()
-    t_enq = time.perf_counter() - t0
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / reps
-    if world > 1:
-        t = torch.tensor([us], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us = float(t.item())
+    reps = 10
+    us, enq = timed(one_step, reps)
+    n_launch = (lib.launches - c0) // reps
     nbytes = sum(int(np.prod(s)) * 4 for _, s in layers)
-    return {'layers': len(layers), 'us_per_step': us, 'launches_per_step': (lib.launches - c0) // reps,
-            'host_enqueue_us_per_step': 1e6 * t_enq / reps,
-            'activation_bytes_read': 3 * nbytes,
-            'note': 'statistics of 53 BN layers forward + backward at batch %d incl. the exchange of '
-                    '2C floats per layer and direction over %d rank(s); device time, host-enqueue '
-                    'bound when us_per_step ~ host_enqueue_us_per_step' % (batch, world)}
+    out = {'layers': len(layers), 'us_per_step': us, 'launches_per_step': n_launch,
+           'host_enqueue_us_per_step': enq, 'activation_bytes_read': 3 * nbytes,
+           'note': 'statistics of 53 BN layers forward + backward at batch %d incl. the exchange of '
+                   '2C floats per layer and direction over %d rank(s) (one kernel per layer and '
+                   'direction); eager calls are host-enqueue-bound (us_per_step ~ '
+                   'host_enqueue_us_per_step); the kernels count their own epochs, so the same 106 '
+                   'launches replay from ONE CUDA graph: us_per_step_graph' % (batch, world)}
+    # the same 106 launches captured once into a CUDA graph (the exchange kernels count their
+    # epochs in device memory, so a replay is a valid collective step)
+    try:
+        side = torch.cuda.Stream()
+        impl.stream = side.cuda_stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_step()
+        side.synchronize()
+        if world > 1:
+            dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            one_step()
+        g.replay()
+        us_g, _ = timed(g.replay, reps)
+        out['us_per_step_graph'] = us_g
+    except Exception as e:      # noqa: BLE001
+        out['graph_error'] = '%s: %s' % (type(e).__name__, e)
+    finally:
+        impl.stream = 0
+    return out
 
 
 def main():

@@ -19,7 +19,7 @@ struct SmallArgs {
   uint32_t* flags[kMaxRanks];
   int rank, n;
   int64_t cap;
-  uint32_t epoch;
+  uint32_t* epoch_ctr;   // this rank's call counter, in DEVICE memory (see small_exchange)
   unsigned long long timeout_ns;
   const float* in;
   float* out;
@@ -32,8 +32,22 @@ struct SmallArgs {
 
 // Called by ALL threads of one CTA.  `in` may have been written by other CTAs of the same
 // grid (the caller has fenced): it is read through L2.
+//
+// The epoch (call number) that tags the flags lives in device memory and is advanced by the
+// kernel itself, not passed as an argument: a launch is therefore REPLAYABLE -- the BN
+// statistics kernels (and with them a whole forward / backward) can be captured into a CUDA
+// graph once and replayed every step.  Collectives of one communicator are issued in the same
+// order on one stream by every rank, so all ranks count alike.
 __device__ __forceinline__ void small_exchange(const SmallArgs& a) {
-  const int par = a.epoch & 1;
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *a.epoch_ctr + 1;
+    *a.epoch_ctr = e;
+    s_epoch = e;
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const int par = epoch & 1;
   // 1. my contribution into slot [rank] of every rank (own included)
   for (int i = threadIdx.x; i < a.n_elems; i += blockDim.x) {
     const float v = __ldcg(a.in + i);
@@ -43,8 +57,8 @@ __device__ __forceinline__ void small_exchange(const SmallArgs& a) {
   __syncthreads();
   if (threadIdx.x < a.n) {
     __threadfence_system();
-    st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
-    spin_until(a.flags[a.rank] + threadIdx.x, a.epoch, a.timeout_ns);
+    st_release_sys(a.flags[threadIdx.x] + a.rank, epoch);
+    spin_until(a.flags[a.rank] + threadIdx.x, epoch, a.timeout_ns);
   }
   __syncthreads();
   // 2. rank-order sum of the N slots, scale, optional variance
@@ -74,7 +88,8 @@ inline void small_args_from(P2PComm* c, SmallArgs* a, double scale) {
   a->rank = c->rank;
   a->n = c->n;
   a->cap = c->small_cap;
-  a->epoch = ++c->small_epoch;
+  // a spare word of this rank's own flag block (zeroed with it)
+  a->epoch_ctr = c->small_flags[c->rank] + 2 * kMaxRanks + 1;
   a->timeout_ns = g_gp_peer_timeout_ns;
   const ScaleArg s = make_scale(scale);
   a->scale_f = s.fs;

@@ -72,6 +72,7 @@ class _Workspace(object):
             nbytes = lib.gp_bn_workspace_bytes(C)
             self.mem = _dev._Allocation(nbytes)
             lib.gp_memset_async(self.mem.ptr, 0, nbytes, 0)
+            lib.gp_stream_synchronize(0)      # zeroed before any stream uses it
             self.C = C
         return self.mem.ptr
 
@@ -103,11 +104,16 @@ def _small_p2p(comm, gdt, n_elems):
 class _NcclImpl(object):
     """``chainermn/functions/batch_normalization.py:35-93``."""
 
-    def __init__(self, comm):
+    def __init__(self, comm, stream=0):
         self.comm = comm
+        #: raw cudaStream_t every launch of this object goes to (0: the legacy default
+        #: stream, what ``chainer.cuda.Stream.null`` is; the torch-based link passes
+        #: torch's current stream, which also makes the calls capturable in a CUDA graph)
+        self.stream = stream
 
     def get_mean_and_var(self, axis, gamma, x, xp=None, interm_dtype=None):
         lib = _lib.get()
+        st = getattr(self, 'stream', 0)
         C = _dev.array_size(gamma)
         N, HW = _check_layout(axis, x, C)
         gdt = _dev.array_dtype(gamma)
@@ -116,7 +122,7 @@ class _NcclImpl(object):
             # one rank: mean and var straight from the statistics kernel (one launch)
             lib.gp_bn_fwd_mean_var(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C,
                                    HW, _dev.device_ptr(buf), _dev.dtype_id(gdt),
-                                   _workspace(self.comm, C), 0)
+                                   _workspace(self.comm, C), st)
             return _halves(buf, C)
         p2p = _small_p2p(self.comm, gdt, 2 * C)
         if p2p is not None:
@@ -125,19 +131,20 @@ class _NcclImpl(object):
             with _lib.nvtx_range('mnbn.fwd_stats+allreduce'):
                 lib.gp_bn_fwd_stats_allreduce(p2p.handle, _dev.device_ptr(x),
                                               _dev.array_dtype_id(x), N, C, HW,
-                                              _dev.device_ptr(buf), _workspace(self.comm, C), 0)
+                                              _dev.device_ptr(buf), _workspace(self.comm, C), st)
             return _halves(buf, C)
         lib.gp_bn_fwd_stats(_dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
-                            _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
-        _allreduce_in_place(self.comm, buf, 2 * C, gdt)
+                            _dev.device_ptr(buf), _dev.dtype_id(gdt), _workspace(self.comm, C), st)
+        _allreduce_in_place(self.comm, buf, 2 * C, gdt, st)
         mean, var = _halves(buf, C)
         # buf *= 1/size; var = sqmean - mean**2 (written over sqmean)
         lib.gp_bn_finish_mean_var(_dev.device_ptr(buf), _dev.dtype_id(gdt), C,
-                                  1.0 / self.comm.size, _dev.device_ptr(var), 0)
+                                  1.0 / self.comm.size, _dev.device_ptr(var), st)
         return mean, var
 
     def get_ggamma_and_gbeta(self, axis, gamma, gy, x_hat, xp=None):
         lib = _lib.get()
+        st = getattr(self, 'stream', 0)
         C = _dev.array_size(gamma)
         N, HW = _check_layout(axis, gy, C)
         gdt = _dev.array_dtype(gamma)
@@ -145,7 +152,7 @@ class _NcclImpl(object):
         lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.array_dtype_id(gy),
                             _dev.device_ptr(x_hat), _dev.array_dtype_id(x_hat),
                             None, None, _lib.GP_F32, N, C, HW, _dev.device_ptr(buf),
-                            _dev.dtype_id(gdt), _workspace(self.comm, C), 0)
+                            _dev.dtype_id(gdt), _workspace(self.comm, C), st)
         buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
         gbeta, ggamma = _halves(buf, C)
         return gbeta, ggamma
@@ -153,20 +160,22 @@ class _NcclImpl(object):
     def _mean_over_ranks(self, buf, n, gdt, like):
         if self.comm.size == 1:
             return buf                     # the mean over one rank
+        st = getattr(self, 'stream', 0)
         p2p = _small_p2p(self.comm, gdt, n)
         if p2p is not None:
             out = _new_like(like, n, gdt)
             p2p.allreduce_small(_dev.device_ptr(buf), _dev.device_ptr(out), n, 0,
-                                1.0 / self.comm.size, None)
+                                1.0 / self.comm.size, st)
             return out
-        _allreduce_in_place(self.comm, buf, n, gdt)
-        _lib.get().gp_scale(_dev.device_ptr(buf), _dev.dtype_id(gdt), n, 1.0 / self.comm.size, 0)
+        _allreduce_in_place(self.comm, buf, n, gdt, st)
+        _lib.get().gp_scale(_dev.device_ptr(buf), _dev.dtype_id(gdt), n, 1.0 / self.comm.size, st)
         return buf
 
     def get_ggamma_and_gbeta_from_x(self, axis, gamma, gy, x, mean, inv_std):
         """Same statistics with ``x_hat = (x - mean) * inv_std`` formed on the
         fly (``_x_hat``), so the caller need not materialise x_hat."""
         lib = _lib.get()
+        st = getattr(self, 'stream', 0)
         C = _dev.array_size(gamma)
         N, HW = _check_layout(axis, gy, C)
         gdt = _dev.array_dtype(gamma)
@@ -179,7 +188,7 @@ class _NcclImpl(object):
                                           _dev.array_dtype_id(x), _dev.device_ptr(mean),
                                           _dev.device_ptr(inv_std),
                                           _dev.array_dtype_id(mean), N, C, HW,
-                                          _dev.device_ptr(buf), _workspace(self.comm, C), 0)
+                                          _dev.device_ptr(buf), _workspace(self.comm, C), st)
             gbeta, ggamma = _halves(buf, C)
             return gbeta, ggamma
         lib.gp_bn_bwd_stats(_dev.device_ptr(gy), _dev.array_dtype_id(gy),
@@ -187,7 +196,7 @@ class _NcclImpl(object):
                             _dev.device_ptr(mean), _dev.device_ptr(inv_std),
                             _dev.array_dtype_id(mean), N, C, HW,
                             _dev.device_ptr(buf), _dev.dtype_id(gdt),
-                            _workspace(self.comm, C), 0)
+                            _workspace(self.comm, C), st)
         buf = self._mean_over_ranks(buf, 2 * C, gdt, gamma)
         gbeta, ggamma = _halves(buf, C)
         return gbeta, ggamma
@@ -286,7 +295,7 @@ class MultiNodeBNImplSelector:
 
 
 def fwd_apply(x, mean, var, gamma, beta, eps, running_mean=None, running_var=None, decay=0.9,
-              adjust=1.0):
+              adjust=1.0, stream=0):
     """Everything of the BN forward that follows the statistics, ONE launch
     (``chainer/functions/normalization/batch_normalization.py:40-77``): ``inv_std =
     rsqrt(var + eps)``, ``y = gamma * (x - mean) * inv_std + beta`` and, when given, the
@@ -304,11 +313,11 @@ def fwd_apply(x, mean, var, gamma, beta, eps, running_mean=None, running_var=Non
                         _dev.device_ptr(inv_std),
                         _dev.device_ptr(running_mean) if running_mean is not None else None,
                         _dev.device_ptr(running_var) if running_var is not None else None,
-                        _dev.dtype_id(rdt), float(decay), float(adjust), 0)
+                        _dev.dtype_id(rdt), float(decay), float(adjust), stream)
     return y, inv_std
 
 
-def bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta):
+def bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta, stream=0):
     """``gx`` of the BN backward, ONE launch with ``x_hat`` formed on the fly
     (``chainer/functions/normalization/batch_normalization.py:105-133``)."""
     lib = _lib.get()
@@ -321,7 +330,7 @@ def bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta):
                         _dev.device_ptr(x), _dev.array_dtype_id(x), N, C, HW,
                         _dev.device_ptr(mean), _dev.device_ptr(inv_std), _dev.device_ptr(gamma),
                         _dev.device_ptr(ggamma), _dev.device_ptr(gbeta), _dev.dtype_id(sdt),
-                        inv_m, _dev.device_ptr(gx), 0)
+                        inv_m, _dev.device_ptr(gx), stream)
     return gx
 
 

@@ -41,6 +41,9 @@ class _MNBNFunction(object):
             def forward(ctx, x, gamma, beta, impl, eps, running_mean, running_var, decay):
                 axis = (0,) + tuple(range(2, x.dim()))
                 x = x.contiguous()
+                # launch on torch's current stream (capturable in a CUDA graph)
+                st = torch.cuda.current_stream().cuda_stream if x.is_cuda else 0
+                impl.stream = st
                 mean, var = impl.get_mean_and_var(axis, gamma, x)
                 # y, inv_std and the running statistics in ONE launch (gp_bn_fwd_apply); m is
                 # the LOCAL element count per channel (chainer/functions/normalization/
@@ -48,7 +51,7 @@ class _MNBNFunction(object):
                 m = x.numel() // gamma.numel()
                 adjust = m / max(m - 1., 1.)
                 y, inv_std = mnbn_functions.fwd_apply(x, mean, var, gamma, beta, eps,
-                                                      running_mean, running_var, decay, adjust)
+                                                      running_mean, running_var, decay, adjust, st)
                 ctx.impl = impl
                 ctx.save_for_backward(x, gamma, mean, inv_std)
                 ctx.mark_non_differentiable(mean, var)
@@ -59,10 +62,12 @@ class _MNBNFunction(object):
                 x, gamma, mean, inv_std = ctx.saved_tensors
                 axis = (0,) + tuple(range(2, x.dim()))
                 gy = gy.contiguous()
+                st = torch.cuda.current_stream().cuda_stream if x.is_cuda else 0
+                ctx.impl.stream = st
                 gbeta, ggamma = ctx.impl.get_ggamma_and_gbeta_from_x(axis, gamma, gy, x, mean,
                                                                      inv_std)
                 # gx in ONE launch, x_hat formed on the fly (gp_bn_bwd_apply)
-                gx = mnbn_functions.bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta)
+                gx = mnbn_functions.bwd_apply(gy, x, mean, inv_std, gamma, ggamma, gbeta, st)
                 return gx, ggamma, gbeta, None, None, None, None, None
 
         cls._fn = MNBN
@@ -140,8 +145,9 @@ class MultiNodeBatchNormalization(link.Link):
             return y
         # fixed statistics (evaluation): the same elementwise kernel, one launch
         with torch.no_grad():
+            st = torch.cuda.current_stream().cuda_stream if x.is_cuda else 0
             y, _ = mnbn_functions.fwd_apply(x.contiguous(), self.avg_mean, self.avg_var, gamma,
-                                            beta, self.eps)
+                                            beta, self.eps, stream=st)
         return y
 
     def start_finetuning(self):

@@ -315,6 +315,34 @@ def main():
                                    rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(bn.avg_var.cpu().numpy(), z['mn|%d|avg_var' % rank],
                                    rtol=1e-4, atol=1e-6)
+    # ---- the statistics + exchange kernel replays from a CUDA graph (device-side epochs) ----
+    if comm._p2p is not None:
+        from chainer_b200.functions.batch_normalization import _NcclImpl
+        impl = _NcclImpl(comm)
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(300 + rank)
+        xg = torch.randn(4, 48, 6, 6, device='cuda', generator=gen)
+        gam = torch.ones(48, device='cuda')
+        m_e, v_e = impl.get_mean_and_var(None, gam, xg)                 # eager, stream 0
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        impl.stream = side.cuda_stream
+        with torch.cuda.stream(side):
+            impl.get_mean_and_var(None, gam, xg)
+        side.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            m_g, v_g = impl.get_mean_and_var(None, gam, xg)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(m_g, m_e) and torch.equal(v_g, v_e), 'graph replay of the MNBN exchange'
+        impl.stream = 0
+        impl.get_mean_and_var(None, gam, xg)                             # and eager again after it
+        torch.cuda.synchronize()
+        dist.barrier()
+
     # ---- AllreducePersistent: running statistics become their mean over the ranks ----
     from chainer_b200.core import link as L
     from chainer_b200.extensions import AllreducePersistent
