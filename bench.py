@@ -80,6 +80,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--legs-deadline-s', type=float, default=300.0,
+                    help='time allowed to the legs that follow the headline (configs[2], img/s); '
+                         'past it the line is printed without them')
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--reference-kind', default='auto', choices=['auto', 'reference', 'port'])
     return ap.parse_args()
@@ -524,6 +527,7 @@ def b200_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
     clocks = sampler.summary(t0, t1)
+    sampler.stop_flag = True
 
     # ---- per-kernel timing (CUDA events around each library launch) --------------
     kern = time_kernels(torch, dist, world, lib, opt, set_grads, reps=min(max(K // 4, 10), 50))
@@ -549,32 +553,6 @@ def b200_main(args):
         except Exception as e:      # noqa: BLE001 -- the device-resident numbers above stand
             e2e = {'value': None, 'unit': 'GB/s', 'h2d_bytes_per_step': n * 4,
                    'd2h_bytes_per_step': n * 4, 'error': '%s: %s' % (type(e).__name__, e)}
-
-    # ---- BASELINE configs[2]: float16 packed buffer + MNBN statistics -------------
-    mnbn = fp16 = None
-    if not args.no_config3 and args.workload == 'resnet50' and args.allreduce_dtype == 'float32':
-        try:
-            fp16 = time_fp16_buffer(torch, dist, world, comm, step, n, optimizer_name, write_grad,
-                                    steps=min(K, 50))
-        except Exception as e:      # noqa: BLE001
-            fp16 = {'error': '%s: %s' % (type(e).__name__, e)}
-        try:
-            mnbn = time_mnbn(torch, dist, world, comm, lib)
-        except Exception as e:      # noqa: BLE001
-            mnbn = {'error': '%s: %s' % (type(e).__name__, e)}
-
-    # ---- the img/s half of the metric -------------------------------------------
-    train = None
-    if not args.no_train and args.workload == 'resnet50':
-        try:
-            train = time_train(torch, dist, rank, world, comm, args)
-        except Exception as e:      # noqa: BLE001
-            train = {'error': '%s: %s' % (type(e).__name__, e)}
-
-    sampler.stop_flag = True
-    if rank != 0:
-        comm.finalize()
-        return
 
     value = world * n * (pack_b + upd_b) / (ms_step * 1e-3) / 1e9
     peaks = {}
@@ -651,20 +629,11 @@ def b200_main(args):
         'host_us_per_step': 1e6 * (t1 - t0) / K,
         'host_enqueue_us_per_step': 1e6 * (t_enq - t0) / K,
     }
-    if train is not None:
-        line['train'] = train
-        if 'img_per_s' in train:
-            line['img_per_s'] = train['img_per_s']
-    if fp16 is not None or mnbn is not None:
-        line['config3'] = {'what': 'BASELINE configs[2]: the same ResNet-50 step with '
-                                   'allreduce_grad_dtype=float16 (fused cast) and the '
-                                   'MultiNodeBatchNormalization statistics of one step',
-                           'float16_buffer': fp16, 'mnbn': mnbn}
     if bus is not None:
         # the step moves S(N+1)/N (multicast) or 2S(N-1)/N (peer memory) bytes per NVLink
         # direction; implied wire rate if the whole step were the exchange
         line['allreduce'] = bus
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
         cms, done, kind = run_cpu_reference(args, plist, sizes, optimizer_name,
                                             budget_s=args.cpu_seconds)
         line['cpu_baseline'] = {
@@ -674,8 +643,69 @@ def b200_main(args):
                 done, args.workload,
                 'unmodified chainermn naive communicator + chainer update_core_cpu, baseline/_ref'
                 if kind == 'reference' else 'NumPy port of the naive communicator + update_core_cpu')}
-    print(json.dumps(line), flush=True)
-    comm.finalize()
+
+    # ---- the legs beside the headline (configs[2], img/s) -------------------------------
+    # Everything the contract needs is in `line` now.  The legs below add to it; they run
+    # under a deadline so that a leg that stops making progress (a peer that died inside an
+    # exchange, say) costs its own numbers, not the line: when the deadline passes, rank 0
+    # prints the line as it stands, with the reason, and every rank leaves.
+    printed = threading.Event()
+
+    def emit():
+        if rank == 0 and not printed.is_set():
+            printed.set()
+            print(json.dumps(line), flush=True)
+
+    def on_deadline():
+        import faulthandler
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        line['legs_error'] = 'the legs after the headline did not finish within %g s; line ' \
+                             'printed without them' % args.legs_deadline_s
+        emit()
+        sys.stdout.flush()
+        os._exit(0)
+    guard = threading.Timer(args.legs_deadline_s, on_deadline)
+    guard.daemon = True
+    guard.start()
+    if _WATCHDOG is not None:
+        _WATCHDOG.cancel()      # the line is safe from here on: the legs' own deadline takes over
+
+    # ---- BASELINE configs[2]: float16 packed buffer + MNBN statistics -------------
+    mnbn = fp16 = None
+    if not args.no_config3 and args.workload == 'resnet50' and args.allreduce_dtype == 'float32':
+        try:
+            fp16 = time_fp16_buffer(torch, dist, world, comm, step, n, optimizer_name, write_grad,
+                                    steps=min(K, 50))
+        except Exception as e:      # noqa: BLE001
+            fp16 = {'error': '%s: %s' % (type(e).__name__, e)}
+        try:
+            mnbn = time_mnbn(torch, dist, world, comm, lib)
+        except Exception as e:      # noqa: BLE001
+            mnbn = {'error': '%s: %s' % (type(e).__name__, e)}
+
+    # ---- the img/s half of the metric -------------------------------------------
+    train = None
+    if not args.no_train and args.workload == 'resnet50':
+        try:
+            train = time_train(torch, dist, rank, world, comm, args)
+        except Exception as e:      # noqa: BLE001
+            train = {'error': '%s: %s' % (type(e).__name__, e)}
+
+    if train is not None:
+        line['train'] = train
+        if 'img_per_s' in train:
+            line['img_per_s'] = train['img_per_s']
+    if fp16 is not None or mnbn is not None:
+        line['config3'] = {'what': 'BASELINE configs[2]: the same ResNet-50 step with '
+                                   'allreduce_grad_dtype=float16 (fused cast) and the '
+                                   'MultiNodeBatchNormalization statistics of one step',
+                           'float16_buffer': fp16, 'mnbn': mnbn}
+    guard.cancel()
+    emit()
+    try:
+        comm.finalize()
+    except Exception as e:      # noqa: BLE001 -- the line is out; a failed leg may have left the context unusable
+        sys.stderr.write('finalize: %s: %s\n' % (type(e).__name__, e))
 
 
 STEP_FUNCS = ('gp_step_momentum_sgd', 'gp_step_adam')
@@ -1213,8 +1243,28 @@ def time_mnbn(torch, dist, world, comm, lib, batch=32):
     return out
 
 
+_WATCHDOG = None
+
+
+def _watchdog_fired():
+    import faulthandler
+    sys.stderr.write('bench.py: no result after BENCH_WATCHDOG_S seconds; stacks follow\n')
+    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+    sys.stderr.flush()
+    os._exit(1)
+
+
 def main():
     args = parse_args()
+    # a bench that stops making progress must say where and end, not sit on the GPU box:
+    # after BENCH_WATCHDOG_S seconds (default 900) every thread's stack goes to stderr and the
+    # process exits (b200_main replaces this by the legs' own deadline once its line is safe)
+    global _WATCHDOG
+    if args.impl == 'b200':
+        _WATCHDOG = threading.Timer(float(os.environ.get('BENCH_WATCHDOG_S', '900')),
+                                    _watchdog_fired)
+        _WATCHDOG.daemon = True
+        _WATCHDOG.start()
     if args.impl == 'reference':
         reference_main(args)
     elif args.impl == 'reference-worker':

@@ -92,6 +92,7 @@ PROTOTYPES = {
     'gp_scale': (c_int, [c_void_p, c_int, c_int64, c_double, c_void_p]),
     'gp_check_finite': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'gp_bn_workspace_bytes': (c_size_t, [c_int64]),
+    'gp_bn_workspace_layout': (c_int, [c_int64, _P(c_int64)]),
     'gp_bn_fwd_stats': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
                                 c_void_p, c_void_p]),
     'gp_bn_fwd_mean_var': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int,

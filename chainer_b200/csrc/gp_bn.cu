@@ -304,8 +304,23 @@ int launch_x(int x_dtype, int gy_dtype, const BnArgs& a, bool vec, dim3 grid, in
   }
 }
 
-size_t ws_counters_bytes(int64_t C) { return (size_t)(((C * 4 + 255) / 256) * 256); }
+// Workspace layout.  ONE workspace serves every BN layer of a communicator, whatever its C, so
+// the words the kernels rely on being ZERO between launches -- the "channels done" counter and
+// the per-channel tickets -- sit in a header whose offsets do not depend on C; the areas that
+// are left holding junk (split partials, staged local statistics) come after it.  (With the
+// C-dependent offsets of round 1 the partials of a C = 64 layer landed on the tickets of a
+// C = 128 layer: those channels were never completed.)
+//   [0, 256)                       "channels done" counter
+//   [256, 256 + 4 * kTicketCap)    channel tickets (splits S > 1 only while C <= kTicketCap)
+//   then                           split partials  [C][kMaxSplits][2] doubles
+//   then                           local 2C float statistics staged for the exchange
+constexpr int64_t kTicketCap = 16384;
+constexpr size_t kWsDoneOff = 0;
+constexpr size_t kWsTicketsOff = 256;
+constexpr size_t kWsPartialsOff = kWsTicketsOff + (size_t)kTicketCap * sizeof(int);
 size_t ws_partials_bytes(int64_t C) { return (size_t)(C * kMaxSplits * 2 * sizeof(double)); }
+size_t ws_local_off(int64_t C) { return kWsPartialsOff + ws_partials_bytes(C); }
+size_t ws_local_bytes(int64_t C) { return (size_t)(2 * C * sizeof(float) + 255) / 256 * 256; }
 
 int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype, const void* mean,
               const void* inv_std, int stat_dtype, int64_t N, int64_t C, int64_t HW, void* out,
@@ -334,9 +349,9 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
                    (long long)comm->small_cap);
       return GP_EINVAL;
     }
-    char* ws = reinterpret_cast<char*>(workspace) + ws_counters_bytes(C) + ws_partials_bytes(C);
-    a.done = reinterpret_cast<int*>(ws);
-    float* local = reinterpret_cast<float*>(ws + 256);
+    char* ws = reinterpret_cast<char*>(workspace);
+    a.done = reinterpret_cast<int*>(ws + kWsDoneOff);
+    float* local = reinterpret_cast<float*>(ws + ws_local_off(C));
     a.out = local;
     a.use_xchg = 1;
     small_args_from(comm, &a.xchg, 1.0 / comm->n);
@@ -357,11 +372,11 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
   if (S > N) S = N;
   if (S > kMaxSplits) S = kMaxSplits;
   if (S < 1) S = 1;
-  if (workspace == nullptr) S = 1;
+  if (workspace == nullptr || C > kTicketCap) S = 1;
   a.rows_per_split = (int)((N + S - 1) / S);
   a.S = (int)((N + a.rows_per_split - 1) / a.rows_per_split);
-  a.counters = reinterpret_cast<int*>(workspace);
-  a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_counters_bytes(C));
+  a.counters = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + kWsTicketsOff);
+  a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kWsPartialsOff);
 
   const int xs = gp_itemsize(x_dtype), gs = gp_itemsize(gy_dtype);
   bool vec = (HW % 4 == 0) && ((uintptr_t)x % (xs == 2 ? 8 : 16) == 0);
@@ -384,10 +399,24 @@ int bn_launch(int mode, const void* x, int x_dtype, const void* gy, int gy_dtype
 
 }  // namespace
 
-// [channel tickets | split partials | "channels done" counter | local 2C statistics]
+// ["channels done" counter | channel tickets | split partials | local 2C statistics]
 extern "C" size_t gp_bn_workspace_bytes(int64_t C) {
   if (C < 0) C = 0;
-  return ws_counters_bytes(C) + ws_partials_bytes(C) + 256 + (size_t)(2 * C * sizeof(float) + 255) / 256 * 256;
+  return ws_local_off(C) + ws_local_bytes(C);
+}
+
+// Byte ranges of the workspace for a layer of C channels, for tests and integrators:
+// out[0..1] the zero-between-launches header, out[2..3] the scratch that may hold junk.
+extern "C" int gp_bn_workspace_layout(int64_t C, int64_t* out4) {
+  if (!out4 || C < 0) {
+    gp_set_error("gp_bn_workspace_layout: bad arguments");
+    return GP_EINVAL;
+  }
+  out4[0] = 0;
+  out4[1] = (int64_t)kWsPartialsOff;
+  out4[2] = (int64_t)kWsPartialsOff;
+  out4[3] = (int64_t)(ws_local_off(C) + ws_local_bytes(C));
+  return 0;
 }
 
 extern "C" int gp_bn_fwd_stats_allreduce(void* p2p_comm, const void* x, int x_dtype, int64_t N,

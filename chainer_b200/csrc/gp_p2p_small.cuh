@@ -41,8 +41,8 @@ struct SmallArgs {
 __device__ __forceinline__ void small_exchange(const SmallArgs& a) {
   __shared__ uint32_t s_epoch;
   if (threadIdx.x == 0) {
-    const uint32_t e = *a.epoch_ctr + 1;
-    *a.epoch_ctr = e;
+    const uint32_t e = __ldcg(a.epoch_ctr) + 1;      // through L2: the previous launch wrote it
+    __stcg(a.epoch_ctr, e);
     s_epoch = e;
   }
   __syncthreads();

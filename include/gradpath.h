@@ -211,9 +211,15 @@ int gp_check_finite(const void* buffer, int dtype, int64_t n_elems, int32_t* d_f
  * _NcclImpl.get_mean_and_var (chainermn/functions/batch_normalization.py:53-56),
  * which reads x twice and materialises square(x).
  * workspace: device scratch of gp_bn_workspace_bytes(C) bytes, zero-initialised
- * once by the caller (the kernel leaves it zeroed again).
+ * once by the caller.  One workspace may serve layers of DIFFERENT C (size it for the
+ * largest), one launch at a time: the words the kernels need zero between launches (the
+ * "channels done" counter and the channel tickets) form a header at C-independent offsets
+ * and are left zeroed; the scratch behind it (split partials, staged local statistics) may
+ * hold junk.  gp_bn_workspace_layout reports both byte ranges: out4 = {header begin, header
+ * end, scratch begin, scratch end for this C}.
  */
 size_t gp_bn_workspace_bytes(int64_t C);
+int gp_bn_workspace_layout(int64_t C, int64_t* out4);
 int gp_bn_fwd_stats(const void* x, int x_dtype, int64_t N, int64_t C, int64_t HW, void* out,
                     int out_dtype, void* workspace, void* stream);
 /* Same pass, single rank: out[0:C] = mean, out[C:2C] = var = sqmean - mean^2

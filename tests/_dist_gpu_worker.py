@@ -343,6 +343,53 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
 
+    # ---- layers of different width share the communicator's ONE statistics workspace:
+    #      every fused statistics + exchange call stays right (and the ranks stay in step)
+    if comm._p2p is not None:
+        from chainer_b200.functions.batch_normalization import _NcclImpl
+        impl = _NcclImpl(comm)
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(900 + rank)
+        shapes = [(32, 64, 56, 56), (32, 128, 28, 28), (32, 256, 14, 14), (32, 512, 28, 28),
+                  (32, 1024, 14, 14), (32, 2048, 7, 7)]
+        data = {}
+        for s in shapes:
+            x = torch.randn(*s, device='cuda', generator=gen) + 0.1 * rank
+            gy = torch.randn(*s, device='cuda', generator=gen) * 1e-3
+            st = torch.stack([x.double().mean(dim=(0, 2, 3)),
+                              (x.double() ** 2).mean(dim=(0, 2, 3))]).cpu()
+            dist.all_reduce(st)                     # gloo: host tensors
+            st = (st / world).cuda()
+            m, v = st[0], st[1] - st[0] * st[0]
+            inv = torch.rsqrt(v + 2e-5)
+            bw = torch.stack([gy.double().sum(dim=(0, 2, 3)),
+                              (gy.double() * (x.double() - m[None, :, None, None])
+                               * inv[None, :, None, None]).sum(dim=(0, 2, 3))]).cpu()
+            dist.all_reduce(bw)
+            bw = (bw / world).cuda()
+            data[s] = (x, gy, torch.ones(s[1], device='cuda'), m, v, inv, bw)
+        impl.get_mean_and_var(None, data[shapes[-1]][2], data[shapes[-1]][0])   # final size
+        for order in (shapes, shapes[::-1], shapes):
+            for s in order:
+                x, gy, gamma, m, v, inv, bw = data[s]
+                mean, var = impl.get_mean_and_var(None, gamma, x)
+                torch.testing.assert_close(mean.double(), m, rtol=1e-5, atol=2e-6, msg=str(s))
+                torch.testing.assert_close(var.double(), v, rtol=1e-5, atol=2e-6, msg=str(s))
+                gbeta, ggamma = impl.get_ggamma_and_gbeta_from_x(None, gamma, gy, x, m.float(),
+                                                                 inv.float())
+                torch.testing.assert_close(gbeta.double(), bw[0], rtol=1e-4, atol=1e-5, msg=str(s))
+                torch.testing.assert_close(ggamma.double(), bw[1], rtol=1e-4, atol=1e-5, msg=str(s))
+                # every rank holds the same bits
+                both = torch.stack([mean, var]).cpu()
+                lo, hi = both.clone(), both.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                assert torch.equal(lo, hi), 'MNBN statistics differ between ranks %s' % (s,)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print('MNBN MIXED-WIDTH WORKSPACE OK')
+
     # ---- AllreducePersistent: running statistics become their mean over the ranks ----
     from chainer_b200.core import link as L
     from chainer_b200.extensions import AllreducePersistent

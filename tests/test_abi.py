@@ -54,3 +54,23 @@ def test_errors_are_reported_without_a_gpu():
         n = ctypes.c_int()
         with pytest.raises(_lib.GradpathError):
             lib.gp_device_count(ctypes.byref(n))      # CUDA error surfaces, no crash
+
+
+def test_bn_workspace_header_does_not_depend_on_the_channel_count():
+    """One statistics workspace serves every BN layer of a communicator.  The words the kernels
+    need ZERO between launches (channels-done counter, channel tickets) must therefore sit at
+    offsets that do not move with C, in front of the scratch that is left holding junk (split
+    partials, staged local statistics) -- otherwise a C = 64 layer's partials land on a C = 128
+    layer's tickets.  Host-side query only, no launch."""
+    import ctypes
+    lib = _lib._Lib(_lib.library_path())
+    seen = None
+    for C in (1, 3, 64, 128, 256, 512, 1024, 2048, 4096, 20000):
+        out = (ctypes.c_int64 * 4)()
+        lib.gp_bn_workspace_layout(C, out)
+        h0, h1, s0, s1 = list(out)
+        assert (h0, h1) == (seen or (h0, h1)), 'header moved with C'
+        seen = (h0, h1)
+        assert h0 == 0 and h1 >= 256 + 4 * min(C, 16384)
+        assert s0 >= h1 and s1 == lib.gp_bn_workspace_bytes(C)
+        assert s1 - s0 >= C * 8          # room for the 2C staged float statistics at least

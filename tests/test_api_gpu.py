@@ -200,6 +200,50 @@ def test_bn_statistics_match_oracle(comm, shape, xdtype):
     np.testing.assert_allclose(gb2.cpu().numpy(), gb_ref, rtol=1e-5, atol=1e-6 * scale)
 
 
+def test_bn_statistics_layers_of_different_width_share_one_workspace(comm):
+    """A model's BN layers all use the communicator's ONE statistics workspace.  Walk the
+    distinct ResNet-50 layer shapes (C = 64 ... 2048, split counts S = 8 ... 1) twice, forward
+    and backward, after the workspace has reached its final size: every call must still be
+    right.  (With a C-dependent workspace layout the split partials of the narrow layers landed
+    on the tickets of the wider ones and those channels were never written.)"""
+    import torch
+    from chainer_b200 import workloads
+    from chainer_b200.functions.batch_normalization import _NcclImpl
+    impl = _NcclImpl(comm)
+    shapes = []
+    for _, s in workloads.resnet50_bn_layers(32):
+        if s not in shapes:
+            shapes.append(s)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(5)
+    data = {}
+    for s in shapes:
+        x = torch.randn(*s, device='cuda', generator=gen) + 0.25
+        gy = torch.randn(*s, device='cuda', generator=gen) * 1e-3
+        x64 = x.double()
+        m = x64.mean(dim=(0, 2, 3))
+        v = (x64 * x64).mean(dim=(0, 2, 3)) - m * m
+        inv = torch.rsqrt(v + 2e-5)
+        gb = gy.double().sum(dim=(0, 2, 3))
+        gg = (gy.double() * (x64 - m[None, :, None, None]) * inv[None, :, None, None]).sum(dim=(0, 2, 3))
+        data[s] = (x, gy, torch.ones(s[1], device='cuda'), m, v, inv, gb, gg,
+                   gy.double().abs().sum(dim=(0, 2, 3)).max().item())
+        del x64
+    # the workspace takes its final size here (widest layer last) ...
+    impl.get_mean_and_var(None, data[shapes[-1]][2], data[shapes[-1]][0])
+    # ... and is then shared by every width, narrow and wide in turn
+    for order in (shapes, shapes[::-1], shapes):
+        for s in order:
+            x, gy, gamma, m, v, inv, gb, gg, scale = data[s]
+            mean, var = impl.get_mean_and_var(None, gamma, x)
+            torch.testing.assert_close(mean.double(), m, rtol=1e-5, atol=2e-6, msg=str(s))
+            torch.testing.assert_close(var.double(), v, rtol=1e-5, atol=2e-6, msg=str(s))
+            gbeta, ggamma = impl.get_ggamma_and_gbeta_from_x(None, gamma, gy, x, m.float(),
+                                                             inv.float())
+            torch.testing.assert_close(gbeta.double(), gb, rtol=1e-4, atol=2e-6 * scale, msg=str(s))
+            torch.testing.assert_close(ggamma.double(), gg, rtol=1e-4, atol=4e-6 * scale, msg=str(s))
+
+
 def test_bn_statistics_deterministic(comm):
     import torch
     from chainer_b200.functions.batch_normalization import _NcclImpl
