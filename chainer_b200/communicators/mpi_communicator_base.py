@@ -8,6 +8,8 @@ The control-plane methods (``*_obj``, ``split``, rank properties, the
 reference's model-parallel functions, which are outside this path; they are
 provided host-staged so that the class is complete, not as a fast path.
 """
+import collections
+
 import numpy as np
 
 from chainer_b200 import config
@@ -33,53 +35,47 @@ def _like(x, host):
     return host
 
 
+_Topology = collections.namedtuple(
+    '_Topology', ['global_rank', 'intra_rank', 'intra_size', 'inter_rank', 'inter_size'])
+
+
+def _from_topology(field):
+    return property(lambda self: getattr(self._topology, field),
+                    doc='``%s`` of this process (``init_ranks``)' % field)
+
+
 class MpiCommunicatorBase(communicator_base.CommunicatorBase):
+
+    #: configuration keys this class owns (name -> default); others go to the base class
+    _OWN_CONFIG = {'batched_copy': False}
 
     def __init__(self, mpi_comm):
         self.mpi_comm = mpi_comm
         self._init_ranks()
         with self.config_scope():
-            self.batched_copy = False
+            for key, default in self._OWN_CONFIG.items():
+                setattr(self, key, default)
 
-    @property
-    def rank(self):
-        return self.mpi_comm.rank
-
-    @property
-    def size(self):
-        return self.mpi_comm.size
-
-    @property
-    def intra_rank(self):
-        return self._intra_rank
-
-    @property
-    def intra_size(self):
-        return self._intra_size
-
-    @property
-    def inter_rank(self):
-        return self._inter_rank
-
-    @property
-    def inter_size(self):
-        return self._inter_size
+    rank = property(lambda self: self.mpi_comm.rank)
+    size = property(lambda self: self.mpi_comm.size)
+    intra_rank = _from_topology('intra_rank')
+    intra_size = _from_topology('intra_size')
+    inter_rank = _from_topology('inter_rank')
+    inter_size = _from_topology('inter_size')
 
     def set_config(self, name, value=True, **kwargs):
-        if name == 'batched_copy':
-            with self.config_scope():
-                self.batched_copy = value
-        else:
+        if name not in self._OWN_CONFIG:
             return super(MpiCommunicatorBase, self).set_config(name, **kwargs)
+        with self.config_scope():
+            setattr(self, name, value)
 
     def get_config(self, name=None):
-        if name == 'batched_copy':
-            return self.batched_copy
-        else:
-            return super(MpiCommunicatorBase, self).get_config(name)
+        if name in self._OWN_CONFIG:
+            return getattr(self, name)
+        return super(MpiCommunicatorBase, self).get_config(name)
 
     def split(self, color, key):
-        return self.__class__(mpi_comm=self.mpi_comm.Split(color, key))
+        return type(self)(mpi_comm=self.mpi_comm.Split(color, key))
 
     # -- ndarray collectives (host staged; outside the gradient path) ---------
     def alltoall(self, xs):
@@ -149,25 +145,26 @@ class MpiCommunicatorBase(communicator_base.CommunicatorBase):
 
     # -- private ---------------------------------------------------------------
     def _init_ranks(self):
-        my_ranks = _communication_utility.init_ranks(self.mpi_comm)
-        assert my_ranks[0] == self.mpi_comm.rank
-        self._intra_rank = my_ranks[1]
-        self._intra_size = my_ranks[2]
-        self._inter_rank = my_ranks[3]
-        self._inter_size = my_ranks[4]
+        topo = _Topology(*_communication_utility.init_ranks(self.mpi_comm)[:5])
+        assert topo.global_rank == self.mpi_comm.rank
+        self._topology = topo
+        # the reference's attribute names, for code that reads them directly
+        self._intra_rank, self._intra_size = topo.intra_rank, topo.intra_size
+        self._inter_rank, self._inter_size = topo.inter_rank, topo.inter_size
 
     def _check_ready_to_allreduce(self, array_a, array_b):
-        my_shapes = ((None if array_a is None else tuple(array_a.shape),
-                      None if array_a is None else str(_dev.array_dtype(array_a))),
-                     tuple(array_b.shape),
-                     str(_dev.array_dtype(array_b)))
-        all_shapes = self.gather_obj((self.rank, my_shapes))
-        if self.rank == 0:
-            for rank, shapes in all_shapes:
-                if my_shapes != shapes:
-                    raise ValueError('Shape does not match: {}'
-                                     ' at rank 0 while {} at rank {}'
-                                     .format(my_shapes, shapes, rank))
+        """Debug mode (``mpi_communicator_base.py:709-728``): rank 0 compares every
+        rank's (shape, dtype) pair of the two buffers with its own."""
+        def describe(a):
+            return (tuple(a.shape), str(_dev.array_dtype(a)))
+        mine = ((None, None) if array_a is None else describe(array_a),) + describe(array_b)
+        gathered = self.gather_obj((self.rank, mine))
+        if self.rank != 0:
+            return
+        for rank, theirs in gathered:
+            if theirs != mine:
+                raise ValueError('Shape does not match: {} at rank 0 while {} at rank {}'
+                                 .format(mine, theirs, rank))
 
     def _ensure_all_finite(self, array):
         if not np.isfinite(_to_host(array)).all():

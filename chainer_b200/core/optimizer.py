@@ -74,37 +74,34 @@ class Hyperparameter(object):
         return getattr(parent, name)
 
     def __repr__(self):
-        d = self.get_dict()
-        keys = sorted(d.keys())
-        values_repr = ', '.join('%s=%s' % (k, d[k]) for k in keys)
-        return 'Hyperparameter(%s)' % values_repr
+        return 'Hyperparameter(%s)' % ', '.join(
+            '%s=%s' % item for item in sorted(self.get_dict().items()))
 
-    @property
-    def parent(self):
-        return self._parent
+    parent = property(lambda self: self._parent)
 
     def get_dict(self):
-        d = {} if self._parent is None else self._parent.get_dict()
-        for k, v in self.__dict__.items():
-            if k != '_parent':
-                d[k] = v
-        return d
+        """Every entry visible from here: ancestors first, nearer ones override."""
+        chain = []
+        node = self
+        while node is not None:
+            chain.append(node)
+            node = node._parent
+        merged = {}
+        for node in reversed(chain):
+            merged.update((k, v) for k, v in node.__dict__.items() if k != '_parent')
+        return merged
 
 
-class HyperparameterProxy(object):
-    """``optimizer.HyperparameterProxy``: alias of ``self.hyperparam.<name>``."""
+class HyperparameterProxy(property):
+    """``optimizer.HyperparameterProxy``: ``obj.<name>`` reads and writes
+    ``obj.hyperparam.<name>`` (a ``property`` whose accessors close over the name)."""
 
     def __init__(self, attr_name):
+        super(HyperparameterProxy, self).__init__(
+            lambda obj: getattr(obj.hyperparam, attr_name),
+            lambda obj, value: setattr(obj.hyperparam, attr_name, value),
+            doc='Alias to ``self.hyperparam.{}``'.format(attr_name))
         self._attr_name = attr_name
-        self.__doc__ = 'Alias to ``self.hyperparam.{}``'.format(attr_name)
-
-    def __get__(self, obj, type=None):
-        if obj is None:
-            return self
-        return getattr(obj.hyperparam, self._attr_name)
-
-    def __set__(self, obj, value):
-        setattr(obj.hyperparam, self._attr_name, value)
 
 
 class _Hookable(object):
@@ -112,36 +109,50 @@ class _Hookable(object):
         self._pre = collections.OrderedDict()
         self._post = collections.OrderedDict()
 
+    def _registry(self, timing):
+        return self._pre if timing == 'pre' else self._post
+
+    def _holder_of(self, name):
+        for reg in (self._pre, self._post):
+            if name in reg:
+                return reg
+        return None
+
     def add_hook(self, hook, name=None, timing='auto'):
+        """Same contract as ``Optimizer.add_hook`` / ``UpdateRule.add_hook``
+        (``optimizer.py:188-224, 693-731``): callable, a known timing ('auto' takes the
+        hook's own ``timing``, 'pre' if it has none), a name that is not taken."""
         if not callable(hook):
             raise TypeError('hook function must be callable')
-        if timing not in ('pre', 'post', 'auto'):
-            raise ValueError("timing must be one of ('pre', 'post', 'auto')")
         if timing == 'auto':
             timing = getattr(hook, 'timing', 'pre')
+        elif timing not in ('pre', 'post'):
+            raise ValueError("timing must be one of ('pre', 'post', 'auto')")
         if name is None:
-            name = getattr(hook, 'name', getattr(hook, '__name__', None))
-            if name is None:
+            for attr in ('name', '__name__'):
+                name = getattr(hook, attr, None)
+                if name is not None:
+                    break
+            else:
                 raise ValueError('the name of the hook function is not specified')
-        if name in self._pre or name in self._post:
+        if self._holder_of(name) is not None:
             raise KeyError('hook "{}" already exists'.format(name))
-        (self._pre if timing == 'pre' else self._post)[name] = hook
+        self._registry(timing)[name] = hook
         _rules_version[0] += 1
 
     def remove_hook(self, name):
-        if name in self._pre:
-            del self._pre[name]
-        elif name in self._post:
-            del self._post[name]
-        else:
+        reg = self._holder_of(name)
+        if reg is None:
             raise KeyError('hook "{}" does not exist'.format(name))
+        del reg[name]
         _rules_version[0] += 1
 
     def has_hooks(self):
-        return bool(self._pre) or bool(self._post)
+        return bool(self._pre or self._post)
 
     def call_hooks(self, timing, args):
-        for hook in list((self._pre if timing == 'pre' else self._post).values()):
+        # a snapshot: hooks may add or remove hooks
+        for hook in tuple(self._registry(timing).values()):
             hook(*args)
 
 
@@ -181,40 +192,48 @@ class UpdateRule(object):
         self.__update(param)
 
     def __update(self, param):
-        # ``optimizer.py:252-305`` without the ChainerX branches
-        is_initialized = param.data is not None
-        loss_scale = getattr(param, '_loss_scale', None)
-        fp32_converted = False
-        param_ = param
-        if self._use_fp32_update and is_initialized and param.dtype == np.float16:
-            # fp32 master weights (``optimizer.py:262-282``): the update runs on a
-            # float32 copy of the parameter with the gradient up-cast to float32
-            from chainer_b200.core.optimizers import _single
-            fp32_param = self.fp32_param_for(param)
-            if param.grad is not None:
-                g32 = _single.new_like(param.grad, np.float32)
-                _single.cast_copy(g32, param.grad)
-                fp32_param.grad = g32
-            else:
-                fp32_param.grad = None
-            param_ = fp32_param
-            fp32_converted = True
-        if is_initialized:
-            self._init_states(param_)
-            if loss_scale is not None and param_.grad is not None:
-                from chainer_b200 import _lib
-                g = param_.grad
-                _lib.get().gp_divide(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
-                                     _dev.array_size(g), float(loss_scale), 0)
-        self._hookable.call_hooks('pre', (self, param_))
-        self.update_core(param_)
-        self._hookable.call_hooks('post', (self, param_))
-        if fp32_converted:
+        # ``optimizer.py:252-305`` without the ChainerX branches, in three stages:
+        # choose the parameter the rule works on, run hooks + rule on it, write back
+        work = self._working_param(param)
+        if param.data is not None:
+            self._init_states(work)
+            self._undo_loss_scale(work, getattr(param, '_loss_scale', None))
+        hooks = self._hookable
+        hooks.call_hooks('pre', (self, work))
+        self.update_core(work)
+        hooks.call_hooks('post', (self, work))
+        if work is not param:
             # ``optimizer.py:297-305``: back to the parameter's dtype (written in place:
             # same values as the reference's ``param.array = fp32.astype(float16)``)
             from chainer_b200.core.optimizers import _single
-            _single.cast_copy(param.data, param_.data)
-            param_.grad = None
+            _single.cast_copy(param.data, work.data)
+            work.grad = None
+
+    def _working_param(self, param):
+        """`param` itself, or -- fp32 update of an initialised float16 parameter
+        (``optimizer.py:262-282``) -- its float32 master copy carrying the gradient
+        up-cast to float32."""
+        if not self._use_fp32_update or param.data is None or param.dtype != np.float16:
+            return param
+        from chainer_b200.core.optimizers import _single
+        master = self.fp32_param_for(param)
+        grad = param.grad
+        if grad is not None:
+            wide = _single.new_like(grad, np.float32)
+            _single.cast_copy(wide, grad)
+            grad = wide
+        master.grad = grad
+        return master
+
+    @staticmethod
+    def _undo_loss_scale(work, loss_scale):
+        """``grad /= loss_scale`` in place (``optimizer.py:286-291``)."""
+        g = work.grad
+        if loss_scale is None or g is None:
+            return
+        from chainer_b200 import _lib
+        _lib.get().gp_divide(_dev.device_ptr(g), _dev.dtype_id(_dev.array_dtype(g)),
+                             _dev.array_size(g), float(loss_scale), 0)
 
     def fp32_param_for(self, param):
         """The float32 master copy of a float16 parameter, created on first use
@@ -351,20 +370,21 @@ class Optimizer(object):
             hook(self)
 
     def loss_scaling(self, interval=1000, scale=None):
-        """``optimizer.py:736-761``."""
-        if scale is None:
-            self._loss_scaling_is_dynamic = True
-            if interval < 1:
-                raise ValueError('interval must be greater than or equal to 1.'
-                                 ' Actual: {}'.format(interval))
-            self._loss_scale = 1.0
-            self._loss_scaling_multiplier = math.pow(2.0, 1.0 / interval)
-            self._loss_scaling_isnan_ever = False
-        else:
-            if scale <= 0:
+        """``optimizer.py:736-761``: a fixed `scale`, or (none given) dynamic scaling that
+        starts at 1 and, once an overflow has been seen, doubles over `interval` steps."""
+        if scale is not None:
+            if not scale > 0:
                 raise ValueError('loss_scale must be a positive number. '
                                  'Actual: {}'.format(scale))
             self._loss_scale = scale
+            return
+        if interval < 1:
+            raise ValueError('interval must be greater than or equal to 1.'
+                             ' Actual: {}'.format(interval))
+        self._loss_scaling_is_dynamic = True
+        self._loss_scaling_isnan_ever = False
+        self._loss_scaling_multiplier = math.pow(2.0, 1.0 / interval)
+        self._loss_scale = 1.0
 
     def set_loss_scale(self, loss_scale):
         self.loss_scaling(scale=loss_scale)
@@ -401,17 +421,17 @@ class Optimizer(object):
         return not getattr(self, '_loss_scaling_isnan', False)
 
     def update_loss_scale(self):
-        """``optimizer.py:781-791``."""
+        """``optimizer.py:781-791``: halve after an overflow; otherwise grow -- by 2 per
+        step until the first overflow ever, by 2^(1/interval) after it; clamp to
+        [1, 65504]."""
         if not self._loss_scaling_is_dynamic:
             return
         if self._loss_scaling_isnan:
-            multiplier = 0.5
-        elif self._loss_scaling_isnan_ever:
-            multiplier = self._loss_scaling_multiplier
+            factor = 0.5
         else:
-            multiplier = 2.0
-        self._loss_scale = max(1, min(self._loss_scale_max,
-                                      self._loss_scale * multiplier))
+            factor = self._loss_scaling_multiplier if self._loss_scaling_isnan_ever else 2.0
+        grown = self._loss_scale * factor
+        self._loss_scale = max(1, grown if grown < self._loss_scale_max else self._loss_scale_max)
 
     def serialize(self, serializer):
         self.t = serializer('t', self.t)
@@ -432,10 +452,11 @@ class GradientMethod(Optimizer):
 
     def setup(self, link):
         super(GradientMethod, self).setup(link)
+        fp32 = self._use_fp32_update
         for param in link.params():
-            param.update_rule = self.create_update_rule()
-            if self._use_fp32_update:
-                param.update_rule.use_fp32_update()
+            rule = param.update_rule = self.create_update_rule()
+            if fp32:
+                rule.use_fp32_update()
         return self
 
     def reallocate_cleared_grads(self):
@@ -449,30 +470,28 @@ class GradientMethod(Optimizer):
         self.reallocate_cleared_grads()
 
     def update(self, lossfun=None, *args, **kwds):
-        """``optimizer.py:857-894``."""
+        """``optimizer.py:857-894``: (forward, clear, backward) when a loss function is
+        given; then overflow check, pre hooks, the parameter updates unless a gradient
+        overflowed, post hooks, and the loss-scale schedule."""
         if lossfun is not None:
-            use_cleargrads = getattr(self, '_use_cleargrads', True)
-            loss = lossfun(*args, **kwds)
-            if use_cleargrads:
-                self.target.cleargrads()
-            else:
-                self.target.zerograds()
-            loss.backward(loss_scale=self._loss_scale)
-            del loss
-
+            self._backward(lossfun, args, kwds)
         self.reallocate_cleared_grads()
         self.check_nan_in_grads()
         self.call_hooks('pre')
-
         self.t += 1
-        if self.is_safe_to_update():
-            if not self._multi_tensor_update():
-                for param in self.target.params():
-                    param.update()
-
+        if self.is_safe_to_update() and not self._multi_tensor_update():
+            for param in self.target.params():
+                param.update()
         self.reallocate_cleared_grads()
         self.call_hooks('post')
         self.update_loss_scale()
+
+    def _backward(self, lossfun, args, kwds):
+        target = self.target
+        loss = lossfun(*args, **kwds)
+        clear = target.cleargrads if getattr(self, '_use_cleargrads', True) else target.zerograds
+        clear()
+        loss.backward(loss_scale=self._loss_scale)
 
     def _multi_tensor_update(self):
         """All parameter updates of this step as ONE launch per (dtype, hyperparameter)
@@ -487,11 +506,12 @@ class GradientMethod(Optimizer):
         self._use_cleargrads = use
 
     def use_fp32_update(self, flag=True):
+        """Switch on for this optimizer and for the rules it has already created
+        (``optimizer.py:817-827``: the rules are switched ON whatever `flag` says)."""
         self._use_fp32_update = flag
-        link = getattr(self, 'target', None)
-        if link is not None:
-            for param in link.params():
-                param.update_rule.use_fp32_update()
+        target = getattr(self, 'target', None)
+        for param in (target.params() if target is not None else ()):
+            param.update_rule.use_fp32_update()
 
     def create_update_rule(self):
         raise NotImplementedError

@@ -30,6 +30,13 @@ def _learning_rate(hp, t):
     return hp.alpha * math.sqrt(1. - math.pow(hp.beta2, t)) / (1. - math.pow(hp.beta1, t))
 
 
+def _renamed_lr(obj, owner):
+    """The deprecated ``lr`` alias of ``alpha_t`` (``adam.py:334-344, 437-446``)."""
+    warnings.warn('{0}.lr has been renamed to AdamRule.alpha_t. '
+                  'Use of {0}.lr is deprecated in Chainer v6.'.format(owner), DeprecationWarning)
+    return obj.alpha_t
+
+
 def _get_intermediate_dtype(dtype):
     """``adam.py:57-63``."""
     if dtype == np.float16:
@@ -68,37 +75,27 @@ class AdamRule(optimizer.UpdateRule):
 
     def _check_eps(self, interm_dtype):
         """``adam.py:176-187``: eps must not underflow in the intermediate dtype."""
-        hp = self.hyperparam
-        eps = interm_dtype(hp.eps)
-        if hp.eps != 0 and eps == 0:
-            raise ValueError(
-                'eps of Adam optimizer is too small for {} ({})'.format(
-                    np.dtype(interm_dtype).name, hp.eps))
+        eps = self.hyperparam.eps
+        if eps != 0 and interm_dtype(eps) == 0:
+            raise ValueError('eps of Adam optimizer is too small for {} ({})'.format(
+                np.dtype(interm_dtype).name, eps))
 
-    @property
-    def alpha_t(self):
-        return _learning_rate(self.hyperparam, self.t)
-
-    @property
-    def lr(self):
-        warnings.warn(
-            'AdamRule.lr has been renamed to AdamRule.alpha_t. '
-            'Use of AdamRule.lr is deprecated in Chainer v6.',
-            DeprecationWarning)
-        return self.alpha_t
+    alpha_t = property(lambda self: _learning_rate(self.hyperparam, self.t))
+    lr = property(lambda self: _renamed_lr(self, 'AdamRule'))
 
     @property
     def bounds(self):
-        """``adam.py:346-358``."""
-        if self.t == 0:
-            raise RuntimeError(
-                'Can\'t determine the bounds of AdaBound optimizer '
-                'because the update steps have not been started.')
+        """AdaBound's (lower, upper) clip of the per-element step at this rule's ``t``
+        (``adam.py:346-358``): both converge to ``final_lr`` (rescaled by how far alpha has
+        moved from its initial value) as ``gamma * t`` grows."""
+        t = self.t
+        if t == 0:
+            raise RuntimeError('Can\'t determine the bounds of AdaBound optimizer '
+                               'because the update steps have not been started.')
         hp = self.hyperparam
-        final_lr = hp.final_lr * hp.alpha / self.initial_alpha
-        lower = final_lr * (1.0 - 1.0 / (hp.gamma * self.t + 1))
-        upper = final_lr * (1.0 + 1.0 / (hp.gamma * self.t))
-        return lower, upper
+        target = hp.final_lr * hp.alpha / self.initial_alpha
+        gt = hp.gamma * t
+        return target * (1.0 - 1.0 / (gt + 1)), target * (1.0 + 1.0 / gt)
 
     def kernel_args(self):
         """(alpha_t, 1-beta1, 1-beta2, eps, eta, wd, lower, upper, flags) for
@@ -156,17 +153,8 @@ class Adam(optimizer.GradientMethod):
     def create_update_rule(self):
         return AdamRule(self.hyperparam)
 
-    @property
-    def alpha_t(self):
-        return _learning_rate(self.hyperparam, self.t)
-
-    @property
-    def lr(self):
-        warnings.warn(
-            'Adam.lr has been renamed to AdamRule.alpha_t. '
-            'Use of Adam.lr is deprecated in Chainer v6.',
-            DeprecationWarning)
-        return self.alpha_t
+    alpha_t = property(lambda self: _learning_rate(self.hyperparam, self.t))
+    lr = property(lambda self: _renamed_lr(self, 'Adam'))
 
 
 for _name in _NAMES:

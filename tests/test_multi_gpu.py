@@ -44,11 +44,12 @@ def test_multi_gpu_path(world_size, transport):
     for r in range(world_size):
         assert 'GPU RANK %d OK' % r in out.stdout
     for line in out.stdout.splitlines():      # the worker's milestones, for the -rA log
-        if line.startswith(('MNBN statistics exchange', 'ONE-LAUNCH STEP OK', 'MULTICAST',
-                            'GPU RANK')):
+        if line.startswith(('MNBN statistics exchange', 'MNBN MIXED-WIDTH', 'ONE-LAUNCH STEP OK',
+                            'MULTICAST', 'GPU RANK')):
             print(line)
     if transport != 'nccl':
         assert 'ONE-LAUNCH STEP OK' in out.stdout
+        assert 'MNBN MIXED-WIDTH WORKSPACE OK' in out.stdout
     if transport == 'multicast':
         if 'MULTICAST UNSUPPORTED' in out.stdout:
             pytest.skip([ln for ln in out.stdout.splitlines() if 'MULTICAST UNSUPPORTED' in ln][0])

@@ -22,6 +22,8 @@ def main():
     ap.add_argument('--profile', action='store_true')
     ap.add_argument('--optimizer', default='momentum_sgd')
     ap.add_argument('--steps', type=int, default=3000)
+    ap.add_argument('--arrays', default='torch', choices=['torch', 'numpy'],
+                    help='torch (CPU tensors: the pointer route a GPU run takes) or numpy arrays')
     ap.add_argument('--scale-elems', type=int, default=400000,
                     help='total elements (the size histogram of ResNet-50 scaled down; host cost '
                          'does not depend on it)')
@@ -43,9 +45,17 @@ def main():
     _lib.set_backend_for_testing(lib)
     plist = workloads.scaled_histogram(args.scale_elems)
     rng = np.random.default_rng(0)
-    model = link_from_named_arrays([(n, rng.standard_normal(s).astype(np.float32)) for n, s in plist])
-    params = [p for _, p in sorted(model.namedparams())]
-    grads = [[np.zeros_like(p.data) for p in params] for _ in range(2)]
+    if args.arrays == 'torch':
+        import torch
+        model = link_from_named_arrays(
+            [(n, torch.from_numpy(rng.standard_normal(s).astype(np.float32))) for n, s in plist])
+        params = [p for _, p in sorted(model.namedparams())]
+        grads = [[torch.zeros_like(p.data) for p in params] for _ in range(2)]
+    else:
+        model = link_from_named_arrays(
+            [(n, rng.standard_normal(s).astype(np.float32)) for n, s in plist])
+        params = [p for _, p in sorted(model.namedparams())]
+        grads = [[np.zeros_like(p.data) for p in params] for _ in range(2)]
     comm = chainer_b200.create_communicator('pure_nccl')
     actual = chainer_b200.MomentumSGD() if args.optimizer == 'momentum_sgd' else chainer_b200.Adam()
     opt = chainer_b200.create_multi_node_optimizer(actual, comm)
