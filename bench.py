@@ -80,7 +80,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-train', action='store_true')
-    ap.add_argument('--legs-deadline-s', type=float, default=300.0,
+    ap.add_argument('--legs-deadline-s', type=float, default=180.0,
                     help='time allowed to the legs that follow the headline (configs[2], img/s); '
                          'past it the line is printed without them')
     ap.add_argument('--no-parity', action='store_true')

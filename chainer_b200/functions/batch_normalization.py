@@ -59,8 +59,13 @@ def _check_layout(axis, x, C):
 
 
 class _Workspace(object):
-    """Per-communicator scratch of the statistics kernels (zero-initialised
-    once; the kernels leave it zeroed)."""
+    """Per-communicator scratch of the statistics kernels, shared by every BN layer of the
+    model whatever its width (zero-initialised once; the kernels leave its header zeroed,
+    see ``gp_bn_workspace_bytes`` in include/gradpath.h).  Sized for 4096 channels up front
+    (about 4 MB) so that its address does not change under a captured CUDA graph; a wider
+    layer still grows it (outside a capture)."""
+
+    MIN_CHANNELS = 4096
 
     def __init__(self):
         self.mem = None
@@ -69,6 +74,7 @@ class _Workspace(object):
     def get(self, C):
         if self.mem is None or C > self.C:
             lib = _lib.get()
+            C = max(int(C), self.MIN_CHANNELS)
             nbytes = lib.gp_bn_workspace_bytes(C)
             self.mem = _dev._Allocation(nbytes)
             lib.gp_memset_async(self.mem.ptr, 0, nbytes, 0)
