@@ -529,6 +529,28 @@ def b200_main(args):
     clocks = sampler.summary(t0, t1)
     sampler.stop_flag = True
 
+    # ---- distribution of single steps (median, p10 / p90) --------------
+    dist_us = None
+    try:
+        n_d = min(max(K, 20), 100)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_d + 1)]
+        barrier()
+        evs[0].record()
+        for k in range(n_d):
+            step(W + K + k)
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        per = np.array([evs[k].elapsed_time(evs[k + 1]) * 1e3 for k in range(n_d)])
+        q = np.percentile(per, [10, 50, 90])
+        if world > 1:
+            t = torch.tensor(q, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            q = t.numpy()
+        dist_us = {'p10': float(q[0]), 'median': float(q[1]), 'p90': float(q[2]), 'steps': n_d,
+                   'note': 'one CUDA event pair per step, outside the timed region; max over ranks'}
+    except Exception as e:      # noqa: BLE001 -- additional information only
+        dist_us = {'error': '%s: %s' % (type(e).__name__, e)}
+
     # ---- per-kernel timing (CUDA events around each library launch) --------------
     kern = time_kernels(torch, dist, world, lib, opt, set_grads, reps=min(max(K // 4, 10), 50))
 
@@ -626,6 +648,7 @@ def b200_main(args):
         'e2e': e2e,
         'gpu_launches': launches,
         'clocks': clocks,
+        'step_us': dist_us,
         'host_us_per_step': 1e6 * (t1 - t0) / K,
         'host_enqueue_us_per_step': 1e6 * (t_enq - t0) / K,
     }
