@@ -672,23 +672,7 @@ def b200_main(args):
     # under a deadline so that a leg that stops making progress (a peer that died inside an
     # exchange, say) costs its own numbers, not the line: when the deadline passes, rank 0
     # prints the line as it stands, with the reason, and every rank leaves.
-    printed = threading.Event()
-
-    def emit():
-        if rank == 0 and not printed.is_set():
-            printed.set()
-            print(json.dumps(line), flush=True)
-
-    def on_deadline():
-        import faulthandler
-        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
-        line['legs_error'] = 'the legs after the headline did not finish within %g s; line ' \
-                             'printed without them' % args.legs_deadline_s
-        emit()
-        sys.stdout.flush()
-        os._exit(0)
-    guard = threading.Timer(args.legs_deadline_s, on_deadline)
-    guard.daemon = True
+    guard = _LegsGuard(line, rank, args.legs_deadline_s)
     guard.start()
     if _WATCHDOG is not None:
         _WATCHDOG.cancel()      # the line is safe from here on: the legs' own deadline takes over
@@ -723,12 +707,47 @@ def b200_main(args):
                                    'allreduce_grad_dtype=float16 (fused cast) and the '
                                    'MultiNodeBatchNormalization statistics of one step',
                            'float16_buffer': fp16, 'mnbn': mnbn}
-    guard.cancel()
-    emit()
+    guard.finish()
     try:
         comm.finalize()
     except Exception as e:      # noqa: BLE001 -- the line is out; a failed leg may have left the context unusable
         sys.stderr.write('finalize: %s: %s\n' % (type(e).__name__, e))
+
+
+class _LegsGuard(object):
+    """Owner of the bench line while the legs beside the headline run.  `finish()` prints the
+    line (rank 0, once).  If it has not been called `deadline_s` seconds after `start()`,
+    every thread's stack goes to stderr, rank 0 prints the line as it stands with
+    `legs_error`, and the process exits 0 -- a leg that stops making progress costs its own
+    numbers, not the line."""
+
+    def __init__(self, line, rank, deadline_s):
+        self.line, self.rank, self.deadline_s = line, rank, deadline_s
+        self._printed = threading.Event()
+        self._timer = threading.Timer(deadline_s, self._expired)
+        self._timer.daemon = True
+
+    def start(self):
+        self._timer.start()
+
+    def _emit(self):
+        if self.rank == 0 and not self._printed.is_set():
+            self._printed.set()
+            print(json.dumps(self.line), flush=True)
+
+    def _expired(self):
+        import faulthandler
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        self.line['legs_error'] = ('the legs after the headline did not finish within %g s; '
+                                   'line printed without them' % self.deadline_s)
+        self._emit()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    def finish(self):
+        self._timer.cancel()
+        self._emit()
 
 
 STEP_FUNCS = ('gp_step_momentum_sgd', 'gp_step_adam')

@@ -54,3 +54,36 @@ def test_reference_arm_other_ranks_print_nothing():
                           '--gpus', '2', '--steps', '1', '--warmup', '1'], cwd=ROOT, env=env,
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def _run_guard(body, rank=0):
+    code = ('import sys, time, json; sys.path.insert(0, %r); import bench\n'
+            'line = {"metric": "m", "value": 1.0}\n'
+            'g = bench._LegsGuard(line, %d, 0.5); g.start()\n' % (ROOT, rank)) + body
+    return subprocess.run([sys.executable, '-c', code], cwd=ROOT, stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=120)
+
+
+def test_bench_line_survives_a_leg_that_never_returns():
+    """A leg beside the headline that stops making progress (a peer lost inside an exchange)
+    must cost its own numbers, not the line: at the deadline rank 0 prints the line as it
+    stands with `legs_error` and exits 0; the stacks go to stderr."""
+    out = _run_guard('time.sleep(60)\nprint("not reached")\n')
+    assert out.returncode == 0
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1 and 'not reached' not in out.stdout
+    line = json.loads(lines[0])
+    assert line['value'] == 1.0 and 'did not finish within 0.5 s' in line['legs_error']
+    assert 'time.sleep' in out.stderr or 'File' in out.stderr       # the stack dump
+    # other ranks leave quietly with the same exit code
+    out = _run_guard('time.sleep(60)\n', rank=1)
+    assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_bench_line_is_printed_once_when_the_legs_finish():
+    out = _run_guard('line["config3"] = {"x": 1}\ng.finish()\ng.finish()\ntime.sleep(1.0)\n')
+    assert out.returncode == 0
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line['config3'] == {'x': 1} and 'legs_error' not in line
