@@ -1299,11 +1299,11 @@ def _watchdog_fired():
 def main():
     args = parse_args()
     # a bench that stops making progress must say where and end, not sit on the GPU box:
-    # after BENCH_WATCHDOG_S seconds (default 900) every thread's stack goes to stderr and the
+    # after BENCH_WATCHDOG_S seconds (default 600) every thread's stack goes to stderr and the
     # process exits (b200_main replaces this by the legs' own deadline once its line is safe)
     global _WATCHDOG
     if args.impl == 'b200':
-        _WATCHDOG = threading.Timer(float(os.environ.get('BENCH_WATCHDOG_S', '900')),
+        _WATCHDOG = threading.Timer(float(os.environ.get('BENCH_WATCHDOG_S', '600')),
                                     _watchdog_fired)
         _WATCHDOG.daemon = True
         _WATCHDOG.start()
